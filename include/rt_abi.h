@@ -1,0 +1,265 @@
+/*
+ * rt_abi.h -- C ABI of the B200 path-tracing render path.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * eazuooz/RayTracinginOneWeekendinCUDA:
+ *
+ *     Render -> RayColor -> BvhNode::Hit / Material::Scatter
+ *     (reference RayTracinginOneWeekend/kernel.cu:65-154)
+ *
+ * The reference has no FFI; the path sits behind (i) the scene-type
+ * constructors used at kernel.cu:203-508, (ii) the Camera constructor
+ * (Camera.h:36-46) and (iii) the launch
+ *     Render<<<grid,8x8>>>(fb, W, H, spp, camera, world, randState)
+ * (kernel.cu:122-124,685-687) followed by host reads of the framebuffer.
+ * (i)+(ii) are kept as host C++ classes (include/rt/scene.hpp); (iii) is
+ * replaced by rt_scene_upload / rt_render / rt_readback below.
+ *
+ * Everything crossing this boundary is plain C: pointers, sizes, PODs.
+ * The scene description is the reference's object graph written out flat
+ * and in FP64 (exactly the numbers the reference's constructors hold), so
+ * that the FP64 oracle and the GPU path consume the same bytes.
+ *
+ * Error convention: every entry point returns RT_OK (0) or a negative
+ * rt_status; nothing calls exit() (the reference does: kernel.cu:31-40).
+ * rt_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef RT_ABI_H
+#define RT_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,     /* bad argument / malformed scene          */
+    RT_ERR_CUDA = -2,        /* a CUDA runtime call failed               */
+    RT_ERR_NO_DEVICE = -3,   /* no usable CUDA device (no CPU fallback)  */
+    RT_ERR_UNSUPPORTED = -4, /* scene uses something the path lacks      */
+    RT_ERR_STATE = -5        /* call order (e.g. readback before render) */
+} rt_status;
+
+/* ---- primitives (Sphere.h:8-21, MovingSphere.h:20-36, Quad.h:25-37) ---- */
+enum { RT_PRIM_SPHERE = 0, RT_PRIM_MOVING_SPHERE = 1, RT_PRIM_QUAD = 2 };
+
+typedef struct rt_prim {
+    int32_t type;        /* RT_PRIM_*                                          */
+    int32_t material;    /* index into rt_scene_desc.materials                 */
+    int32_t first_xform; /* instance chain, outermost first (Instance.h:28,71) */
+    int32_t xform_count; /* 0 = not instanced                                  */
+    double a[3];         /* sphere: centre | moving: centre0 | quad: Q         */
+    double b[3];         /* moving: centre1                  | quad: u         */
+    double c[3];         /*                                  | quad: v         */
+    double radius;       /* spheres                                            */
+    double time0, time1; /* moving sphere shutter interval                     */
+} rt_prim;
+
+/* ---- instance wrappers (Instance.h:28-64 Translate, :71-159 RotateY) ---- */
+enum { RT_XFORM_TRANSLATE = 0, RT_XFORM_ROTATE_Y = 1 };
+
+typedef struct rt_xform {
+    int32_t type;    /* RT_XFORM_*                                       */
+    int32_t _pad;
+    double v[3];     /* translate: offset | rotate_y: {sin, cos, degrees} */
+} rt_xform;
+
+/* ---- top-level list[] entries: what the reference hands to BvhNode ---- */
+enum {
+    RT_OBJ_PRIM = 0,  /* one primitive (possibly instanced)                    */
+    RT_OBJ_LIST = 1,  /* owning HittableList tested linearly (HittableList.h)  */
+    RT_OBJ_MEDIUM = 2 /* ConstantMedium over a boundary (ConstantMedium.h)     */
+};
+
+typedef struct rt_object {
+    int32_t kind;           /* RT_OBJ_*                                        */
+    int32_t first_prim;     /* prims of the object / of the medium's boundary  */
+    int32_t prim_count;
+    int32_t phase_material; /* medium: its Isotropic material                  */
+    int32_t medium_id;      /* medium: construction order, keys its RNG draws  */
+    int32_t _pad;
+    double density;         /* medium: rho (ConstantMedium.h:22)               */
+    double bbox[6];         /* xmin,xmax,ymin,ymax,zmin,zmax as the reference's
+                               constructor chain computes it (AABB.h:26-48)    */
+} rt_object;
+
+/* ---- materials (Material.h:45-167, Metal.h:9-35, Dielectric.h:10-69) ---- */
+enum {
+    RT_MAT_LAMBERTIAN = 0,
+    RT_MAT_METAL = 1,
+    RT_MAT_DIELECTRIC = 2,
+    RT_MAT_DIFFUSE_LIGHT = 3,
+    RT_MAT_ISOTROPIC = 4
+};
+
+typedef struct rt_material {
+    int32_t type;     /* RT_MAT_*                                     */
+    int32_t texture;  /* lambertian / light / isotropic: texture index */
+    double albedo[3]; /* metal                                         */
+    double fuzz;      /* metal, already min(fuzz,1) (Metal.h:13)       */
+    double ior;       /* dielectric                                    */
+} rt_material;
+
+/* ---- textures (Texture.h:35-176) ---- */
+enum { RT_TEX_SOLID = 0, RT_TEX_CHECKER = 1, RT_TEX_IMAGE = 2, RT_TEX_NOISE = 3 };
+
+typedef struct rt_texture {
+    int32_t type;    /* RT_TEX_*                                           */
+    int32_t even;    /* checker: texture index                             */
+    int32_t odd;     /* checker: texture index                             */
+    int32_t image;   /* image: index into images, -1 = none (-> cyan)      */
+    int32_t perlin;  /* noise: index into perlins                          */
+    int32_t _pad;
+    double color[3]; /* solid                                              */
+    double scale;    /* checker: 1/scale is applied (Texture.h:65) | noise */
+} rt_texture;
+
+/* Perlin tables (Perlin.h:22-34, 84-117): 256 unit vectors + 3 perms. */
+typedef struct rt_perlin {
+    double ranvec[256][3];
+    int32_t perm_x[256];
+    int32_t perm_y[256];
+    int32_t perm_z[256];
+} rt_perlin;
+
+/* RGB8 texels as RtwImage hands them to ImageTexture (RtwImage.h:51-105):
+ * already linearised and re-quantised; row 0 = top of the image. */
+typedef struct rt_image {
+    int32_t width, height;
+    const uint8_t* rgb; /* width*height*3 bytes, may be NULL (-> cyan) */
+} rt_image;
+
+typedef struct rt_scene_desc {
+    int32_t abi_version; /* RT_ABI_VERSION */
+    int32_t n_objects, n_prims, n_xforms, n_materials, n_textures, n_perlins, n_images;
+    const rt_object* objects; /* in list[] construction order (kernel.cu:207-508) */
+    const rt_prim* prims;
+    const rt_xform* xforms;
+    const rt_material* materials;
+    const rt_texture* textures;
+    const rt_perlin* perlins;
+    const rt_image* images;
+} rt_scene_desc;
+
+/* Camera surface (Camera.h:36-46 + kernel.cu:189-197), in the current book's
+ * parameterisation; the reference's `aperture` is
+ *     aperture = 2 * focus_dist * tan(defocus_angle/2)      (degrees in)
+ * so aperture 0.1 at focus_dist 10 is defocus_angle = 2*atan(0.005) rad.
+ * If aperture >= 0 it overrides defocus_angle (exact reference mapping). */
+typedef struct rt_camera {
+    int32_t image_width, image_height; /* aspect = width/height (kernel.cu:536) */
+    int32_t samples_per_pixel;
+    int32_t max_depth;                 /* reference hard-codes 50 (kernel.cu:71) */
+    double vfov;                       /* degrees */
+    double lookfrom[3], lookat[3], vup[3];
+    double defocus_angle;              /* degrees */
+    double focus_dist;
+    double aperture;                   /* < 0: derive from defocus_angle */
+    double time0, time1;               /* shutter */
+    double background[3];              /* constant colour (kernel.cu:77,197) */
+} rt_camera;
+
+/* Kernel variants (rt_render_params.variant). */
+enum {
+    RT_VARIANT_AUTO = 0,      /* pick per scene class                          */
+    RT_VARIANT_MEGAKERNEL = 1, /* persistent-thread megakernel                  */
+    RT_VARIANT_WAVEFRONT = 2   /* ray-gen / extend / shade queues               */
+};
+
+/* BVH the device traverses (rt_render_params.bvh / rt_upload_options.bvh). */
+enum {
+    RT_BVH_SAH = 0,       /* binned-SAH tree over baked world-space primitives  */
+    RT_BVH_REFERENCE = 1, /* the reference's median-split topology (BvhNode.h)  */
+    RT_BVH_NONE = 2       /* linear list: the reference's own BVH==list check   */
+};
+
+typedef struct rt_upload_options {
+    int32_t device; /* CUDA device ordinal */
+    int32_t bvh;    /* RT_BVH_* */
+    int32_t max_leaf_prims; /* 0 = default */
+    int32_t _pad;
+} rt_upload_options;
+
+typedef struct rt_render_params {
+    int32_t sample_begin, sample_end; /* global sample indices rendered by this call:
+                                         GPU k of G renders [k*spp/G,(k+1)*spp/G)   */
+    uint32_t seed;                    /* reference uses 1984 (kernel.cu:118)         */
+    int32_t variant;                  /* RT_VARIANT_*                                */
+    int32_t clear;                    /* 1: zero the accumulator + ray counter first */
+    int32_t block_threads;            /* 0 = default                                 */
+    int32_t blocks_per_sm;            /* 0 = default                                 */
+    int32_t flags;                    /* RT_FLAG_*                                   */
+    void* stream;                     /* cudaStream_t to launch on, NULL = default   */
+    float* accum;                     /* optional caller-owned device buffer W*H*3
+                                         fp32 (e.g. a torch tensor for NCCL); NULL =
+                                         the handle's own accumulator                */
+} rt_render_params;
+
+enum {
+    RT_FLAG_FP32_POSITIONS = 1 /* ablation: keep hit positions in fp32 (default FP64) */
+};
+
+typedef struct rt_scene_s* rt_scene_handle;
+
+/* Per-ray traversal statistics gathered by an instrumented render (debug). */
+typedef struct rt_stats {
+    uint64_t rays;       /* world.Hit queries = RayColor loop iterations (kernel.cu:71-74) */
+    uint64_t paths;      /* camera samples started                                         */
+    uint64_t node_tests; /* box tests executed on device                                   */
+    uint64_t prim_tests; /* primitive tests executed on device                             */
+} rt_stats;
+
+/* Deep-copies the host scene, bakes instances, builds the device BVH and
+ * uploads everything to `opt->device`. Replaces CreateWorld<<<1,1>>>
+ * (kernel.cu:176-543, launched :667) + the cudaMallocs at :628-649. */
+int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt_scene_handle* out);
+
+/* Replaces RenderInit + Render launches (kernel.cu:681-689). Asynchronous on
+ * p->stream; adds fp32 linear radiance SUMS for samples [begin,end) into the
+ * accumulator (row 0 = bottom row, like the reference framebuffer). */
+int rt_render(rt_scene_handle scene, const rt_camera* cam, const rt_render_params* p);
+
+/* Device pointer + float count of the handle's accumulator (for collectives). */
+int rt_accum_ptr(rt_scene_handle scene, float** dev_ptr, uint64_t* n_floats);
+
+/* Blocks until the handle's queued work is done. */
+int rt_sync(rt_scene_handle scene);
+
+/* Replaces the host reads of the managed framebuffer (kernel.cu:707).
+ * linear_rgb (W*H*3 floats, may be NULL): mean radiance = sum / cam.samples_per_pixel.
+ * srgb8 (W*H*3 bytes, may be NULL): sqrt-gamma (kernel.cu:150-152) then
+ *   clamp[0,0.999]*256 quantise (kernel.cu:712-718); row 0 = TOP row (PPM order).
+ * `accum`: device buffer to read instead of the handle's (may be NULL). */
+int rt_readback(rt_scene_handle scene, const float* accum, float* linear_rgb, uint8_t* srgb8,
+                rt_stats* stats);
+
+int rt_scene_free(rt_scene_handle scene);
+
+/* Scene summary after upload (prim/node counts, bytes, kernel class). */
+typedef struct rt_scene_info {
+    int32_t n_prims_baked, n_nodes, n_media, max_depth_bvh;
+    int32_t features;      /* RT_FEAT_* bitmask that selected the kernel instantiation */
+    int32_t scene_in_smem; /* 1 when nodes+prims+materials are staged in shared memory */
+    uint64_t device_bytes;
+    int32_t medium_visits[8]; /* T2: reference-topology visit multiplicity per medium_id */
+} rt_scene_info;
+int rt_scene_get_info(rt_scene_handle scene, rt_scene_info* info);
+
+const char* rt_last_error(void);
+
+/* Test hook: one uniform of the render stream, exactly as the kernel draws it:
+ * (0,1], keyed on (seed, pixel, sample, slot, domain, dim). */
+float rt_rng_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t domain,
+                     uint32_t dim);
+
+/* Writes the reference's P3 text PPM (kernel.cu:696-723) from srgb8 (top row first). */
+int rt_write_ppm(const char* path, const uint8_t* srgb8, int32_t width, int32_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_ABI_H */
