@@ -167,7 +167,6 @@ def build_ref_stream(tmp: str) -> None:
 
 GPU_PROLOGUE = r'''
 // ---- added by oracle/build_ref.py (not reference code) ----
-__device__ unsigned long long gRtRayCount = 0ULL;
 __global__ void RtDumpBoxes(Hittable** list, int n)
 {
     for (int i = 0; i < n; i++) {
@@ -247,10 +246,14 @@ def gpu_source() -> str:
     src = sub_once(src, ws("for (int j = imageHeight - 1; j >= 0; j--) { std::cerr"),
                    "for (int j = ppmPath ? imageHeight - 1 : -1; j >= 0; j--)\n\t{\n\t\tif (0) std::cerr",
                    "gpu ppm loop")
-    return "#include <cstdio>\n#include <cstdlib>\n" + src
+    return ("#include <cstdio>\n#include <cstdlib>\n"
+            "__device__ unsigned long long gRtRayCount = 0ULL; // added by oracle/build_ref.py\n" + src)
 
 
 def build_ref_gpu(tmp: str) -> None:
+    # its own directory: kernel.cu's quote-includes must find the UNPATCHED headers via -I
+    tmp = os.path.join(tmp, "gpu")
+    os.makedirs(tmp, exist_ok=True)
     with open(os.path.join(tmp, "ref_gpu.cu"), "w", encoding="utf-8") as f:
         f.write(gpu_source())
     run(["g++", "-O2", "-w", "-c", os.path.join(RT, "StbImageImpl.cpp"), "-o", os.path.join(tmp, "stb_exe.o")])

@@ -1,0 +1,669 @@
+// rt_device.cu -- kernels and the device half of the C ABI (include/rt_abi.h).
+//
+// Replaces the reference's RenderInit + Render launches and the device-side
+// object graph they walk (reference kernel.cu:110-154, launched :681-689).
+//
+// Megakernel design (sm_100a, 148 SMs):
+//   * persistent CTAs, one per SM by default; each warp pulls 8x4-pixel tiles
+//     from a global atomic counter, so long tiles do not stall a whole block
+//     the way the reference's 8x8 blocks do;
+//   * inside a tile every lane owns one pixel and runs a flat state machine
+//     "regenerate if dead -> trace one ray -> shade": a lane whose path ends
+//     starts its next sample at once instead of idling until the slowest path
+//     of the warp finishes (the reference nests spp loop > bounce loop > BVH
+//     loop, kernel.cu:138-144 / :71-95 / BvhNode.h:113-155);
+//   * when nodes + primitives + materials fit, they are staged once per CTA in
+//     shared memory (Book 1: ~50 KB) and traversal runs on LDS.128; otherwise
+//     LDG.E.128 through the read-only path with the set resident in L1/L2;
+//   * the traversal stack lives in shared memory, [level][thread];
+//   * no per-pixel RNG state: every uniform is a hash of
+//     (seed, pixel, sample, slot, domain, dim) -- include/rt_rng.h;
+//   * radiance is summed in fp32 registers per pixel in sample order and added
+//     to the fp32 accumulator once per tile (deterministic, no atomics).
+// No CPU fallback: without a CUDA device every entry point returns an error.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_abi.h"
+#include "rt_pack.hpp"
+#include "rt_trace.cuh"
+
+void rt_set_error(const char* fmt, ...); // rt_error.cpp
+
+#define RT_CUDA(call)                                                                               \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            rt_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return RT_ERR_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+namespace {
+
+using namespace rtdev;
+
+constexpr int kStackLevels = 32;
+constexpr int kTileW = 8, kTileH = 4;
+
+struct RenderArgs {
+    float* accum;              // W*H*3 fp32 sums, row 0 = bottom
+    unsigned long long* stats; // [0] rays [1] paths [2] node tests [3] prim tests
+    unsigned int* tileCounter;
+    int sampleBegin, sampleEnd;
+    uint32_t seed;
+    int tilesX, tilesY;
+    // byte sizes of the staged arrays (SMEM variant)
+    uint32_t nodesBytes, spheresBytes, sphereMatBytes, movingBytes, quadsBytes, mediaBytes, materialsBytes;
+};
+
+__device__ __forceinline__ uint32_t SmemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t Stage(uint32_t& cursor, char* smem, const void* src, uint32_t bytes)
+{
+    const uint32_t at = cursor;
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(smem + at);
+    for (uint32_t k = threadIdx.x; k < bytes / 16u; k += blockDim.x) d[k] = __ldg(&s[k]);
+    cursor += (bytes + 15u) & ~15u;
+    return at;
+}
+
+template <int FEAT, bool SMEM, bool STATS>
+__global__ void RenderMega(const DevScene scene, const DevCamera cam, const RenderArgs args)
+{
+    extern __shared__ __align__(16) char smem[];
+    const uint32_t smemBase = SmemAddr(smem);
+    uint32_t cursor = blockDim.x * 4u * kStackLevels;
+
+    SceneView<SMEM> sv;
+    if constexpr (SMEM) {
+        sv.nodes.a = smemBase + Stage(cursor, smem, scene.nodes, args.nodesBytes);
+        sv.spheres.a = smemBase + Stage(cursor, smem, scene.spheres, args.spheresBytes);
+        sv.sphere_material.a = smemBase + Stage(cursor, smem, scene.sphere_material, args.sphereMatBytes);
+        sv.moving.a = smemBase + Stage(cursor, smem, scene.moving, args.movingBytes);
+        sv.quads.a = smemBase + Stage(cursor, smem, scene.quads, args.quadsBytes);
+        sv.media.a = smemBase + Stage(cursor, smem, scene.media, args.mediaBytes);
+        sv.materials.a = smemBase + Stage(cursor, smem, scene.materials, args.materialsBytes);
+        __syncthreads();
+    } else {
+        sv.nodes.a = reinterpret_cast<const char*>(scene.nodes);
+        sv.spheres.a = reinterpret_cast<const char*>(scene.spheres);
+        sv.sphere_material.a = reinterpret_cast<const char*>(scene.sphere_material);
+        sv.moving.a = reinterpret_cast<const char*>(scene.moving);
+        sv.quads.a = reinterpret_cast<const char*>(scene.quads);
+        sv.media.a = reinterpret_cast<const char*>(scene.media);
+        sv.materials.a = reinterpret_cast<const char*>(scene.materials);
+    }
+    sv.textures = scene.textures;
+    sv.perlins = scene.perlins;
+    sv.images = scene.images;
+    sv.root_ref = scene.root_ref;
+
+    Stack stack;
+    stack.base = smemBase + threadIdx.x * 4u;
+    stack.stride = blockDim.x * 4u;
+
+    const int lane = threadIdx.x & 31;
+    const int nTiles = args.tilesX * args.tilesY;
+    const f3 background = make_f3(cam.background[0], cam.background[1], cam.background[2]);
+    unsigned long long nRays = 0, nPaths = 0, nNode = 0, nPrim = 0;
+
+    while (true) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(args.tileCounter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= nTiles) break;
+        const int tx = tile % args.tilesX, ty = tile / args.tilesX;
+        const int i = tx * kTileW + (lane & (kTileW - 1));
+        const int j = ty * kTileH + (lane / kTileW);
+        const bool valid = i < cam.width && j < cam.height;
+        const uint32_t pixel = (uint32_t)(j * cam.width + i);
+
+        f3 sum = make_f3(0.0f, 0.0f, 0.0f);
+        f3 throughput = make_f3(1.0f, 1.0f, 1.0f);
+        Ray ray;
+        ray.o.x = ray.o.y = ray.o.z = 0.0;
+        ray.d.x = ray.d.y = ray.d.z = 1.0;
+        ray.time = 0.0f;
+        int sample = args.sampleBegin;
+        int bounce = 0;
+        bool alive = false;
+        bool done = !valid;
+
+        while (true) {
+            if (!alive && !done) {
+                if (sample >= args.sampleEnd) {
+                    done = true;
+                } else {
+                    DrawStream rng;
+                    rng.Begin(args.seed, pixel, (uint32_t)sample, 0u);
+                    ray = CameraRay(cam, i, j, rng);
+                    throughput = make_f3(1.0f, 1.0f, 1.0f);
+                    bounce = 0;
+                    alive = true;
+                    if (STATS) ++nPaths;
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+            if (alive) {
+                uint32_t nodeTests = 0, primTests = 0;
+                const TraceResult tr = Trace<FEAT, SMEM>(sv, ray, 0.001f, stack, args.seed, pixel, (uint32_t)sample,
+                                                         (uint32_t)bounce + 1u, nodeTests, primTests);
+                ++nRays;
+                if (STATS) {
+                    nNode += nodeTests;
+                    nPrim += primTests;
+                }
+                if (tr.hit == RT_HIT_NONE) {
+                    // kernel.cu:74-79
+                    sum = sum + throughput * background;
+                    alive = false;
+                    ++sample;
+                } else {
+                    Hit h;
+                    FinalizeHit<FEAT, SMEM>(sv, ray, tr, h);
+                    const uint32_t type = RT_HIT_TYPE(tr.hit);
+                    const bool sphereLike = type == RT_LEAF_SPHERE || type == RT_LEAF_MOVING;
+                    DrawStream rng;
+                    rng.Begin(args.seed, pixel, (uint32_t)sample, (uint32_t)bounce + 1u);
+                    f3 atten, dir, emitted;
+                    const f3 dirIn = make_f3((float)ray.d.x, (float)ray.d.y, (float)ray.d.z);
+                    const bool scattered = Scatter<FEAT, SMEM>(sv, h, dirIn, sphereLike, rng, atten, dir, emitted);
+                    // kernel.cu:82-83
+                    sum = sum + throughput * emitted;
+                    if (!scattered) {
+                        alive = false;
+                        ++sample;
+                    } else {
+                        // kernel.cu:93-94
+                        throughput = throughput * atten;
+                        ray.o = h.p;
+                        ray.d.x = (double)dir.x;
+                        ray.d.y = (double)dir.y;
+                        ray.d.z = (double)dir.z;
+                        if (++bounce >= cam.max_depth) { // kernel.cu:71,97
+                            alive = false;
+                            ++sample;
+                        }
+                    }
+                }
+            }
+        }
+        if (valid) {
+            float* px = args.accum + (size_t)pixel * 3u;
+            px[0] += sum.x;
+            px[1] += sum.y;
+            px[2] += sum.z;
+        }
+    }
+
+    // one atomic per warp for the counters
+    for (int off = 16; off > 0; off >>= 1) {
+        nRays += __shfl_down_sync(0xffffffffu, nRays, off);
+        if (STATS) {
+            nPaths += __shfl_down_sync(0xffffffffu, nPaths, off);
+            nNode += __shfl_down_sync(0xffffffffu, nNode, off);
+            nPrim += __shfl_down_sync(0xffffffffu, nPrim, off);
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&args.stats[0], nRays);
+        if (STATS) {
+            atomicAdd(&args.stats[1], nPaths);
+            atomicAdd(&args.stats[2], nNode);
+            atomicAdd(&args.stats[3], nPrim);
+        }
+    }
+}
+
+// kernel.cu:147-153 (mean, sqrt gamma) + :712-718 (clamp to [0,0.999], *256),
+// fused with the row flip to PPM order (kernel.cu:699: top row first).
+__global__ void ResolveKernel(const float* __restrict__ accum, float* __restrict__ linearOut, uint8_t* __restrict__ srgbOut,
+                              int width, int height, float invSpp)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = width * height;
+    if (idx >= n) return;
+    const float r = accum[idx * 3 + 0] * invSpp, g = accum[idx * 3 + 1] * invSpp, b = accum[idx * 3 + 2] * invSpp;
+    if (linearOut) {
+        linearOut[idx * 3 + 0] = r;
+        linearOut[idx * 3 + 1] = g;
+        linearOut[idx * 3 + 2] = b;
+    }
+    if (srgbOut) {
+        const int i = idx % width, j = idx / width;
+        const int o = ((height - 1 - j) * width + i) * 3;
+        const float c[3] = {sqrtf(r), sqrtf(g), sqrtf(b)};
+        for (int k = 0; k < 3; ++k) {
+            const float v = c[k] < 0.0f ? 0.0f : (c[k] > 0.999f ? 0.999f : c[k]);
+            srgbOut[o + k] = (uint8_t)(int)(256.0f * v);
+        }
+    }
+}
+
+using KernelFn = void (*)(const DevScene, const DevCamera, const RenderArgs);
+
+template <int FEAT> KernelFn PickKernel(bool smem, bool stats)
+{
+    if (smem) return stats ? RenderMega<FEAT, true, true> : RenderMega<FEAT, true, false>;
+    return stats ? RenderMega<FEAT, false, true> : RenderMega<FEAT, false, false>;
+}
+
+// Instantiations: spheres only / + moving spheres and textures / everything.
+constexpr int kFeatSpheres = 0;
+constexpr int kFeatMotion = RT_FEAT_MOVING | RT_FEAT_TEXTURE;
+constexpr int kFeatAll = RT_FEAT_MOVING | RT_FEAT_QUAD | RT_FEAT_MEDIUM | RT_FEAT_TEXTURE;
+
+KernelFn PickKernelForFeatures(int features, bool smem, bool stats, int* picked)
+{
+    if (features == 0) {
+        *picked = kFeatSpheres;
+        return PickKernel<kFeatSpheres>(smem, stats);
+    }
+    if ((features & ~kFeatMotion) == 0) {
+        *picked = kFeatMotion;
+        return PickKernel<kFeatMotion>(smem, stats);
+    }
+    *picked = kFeatAll;
+    return PickKernel<kFeatAll>(smem, stats);
+}
+
+template <class T> int UploadVec(const std::vector<T>& v, T** dev, uint64_t* bytes)
+{
+    *dev = nullptr;
+    // always allocate at least one record so staging code can read 16 bytes
+    const size_t n = v.empty() ? 1 : v.size();
+    const size_t sz = ((n * sizeof(T) + 15) / 16) * 16;
+    RT_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), sz));
+    RT_CUDA(cudaMemset(*dev, 0, sz));
+    if (!v.empty()) RT_CUDA(cudaMemcpy(*dev, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *bytes += sz;
+    return RT_OK;
+}
+
+} // namespace
+
+struct rt_scene_s {
+    int device = 0;
+    DevScene dev{};
+    rtpack::Packed* host = nullptr; // kept for sizes / info
+    std::vector<void*> allocations;
+    std::vector<DevImage> images;
+    uint64_t deviceBytes = 0;
+    bool fitsSmem = false;
+    uint32_t stagedBytes = 0;
+    int smCount = 0;
+    int maxSmemOptin = 0;
+    // accumulator + counters
+    float* accum = nullptr;
+    size_t accumFloats = 0;
+    float* linearStage = nullptr;
+    uint8_t* srgbStage = nullptr;
+    unsigned long long* stats = nullptr;
+    unsigned int* tileCounter = nullptr;
+    cudaStream_t lastStream = nullptr;
+    rt_camera lastCam{};
+    bool rendered = false;
+    int pickedFeatures = 0;
+};
+
+extern "C" {
+
+int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt_scene_handle* out)
+{
+    if (!scene || !out) {
+        rt_set_error("rt_scene_upload: NULL argument");
+        return RT_ERR_INVALID;
+    }
+    *out = nullptr;
+    rt_upload_options o{};
+    if (opt) o = *opt;
+    // host work first (validation, baking, BVH): a malformed scene is reported
+    // as such even on a machine without a GPU
+    rtpack::Packed* packed = nullptr;
+    try {
+        rtpack::Packer pk(*scene, o);
+        pk.Run();
+        packed = new rtpack::Packed(std::move(pk.out));
+    } catch (const std::exception& e) {
+        rt_set_error("rt_scene_upload: %s", e.what());
+        return RT_ERR_INVALID;
+    }
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev <= 0) {
+        delete packed;
+        rt_set_error("rt_scene_upload: no CUDA device available (this library has no CPU path)");
+        return RT_ERR_NO_DEVICE;
+    }
+    if (o.device < 0 || o.device >= nDev) {
+        delete packed;
+        rt_set_error("rt_scene_upload: device %d out of range (have %d)", o.device, nDev);
+        return RT_ERR_INVALID;
+    }
+    RT_CUDA(cudaSetDevice(o.device));
+    rt_scene_s* h = new rt_scene_s();
+    h->device = o.device;
+    h->host = packed;
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, o.device));
+    h->smCount = prop.multiProcessorCount;
+    h->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
+
+#define RT_UP(field, vec, T)                                                         \
+    do {                                                                             \
+        T* p_ = nullptr;                                                             \
+        int rc_ = UploadVec<T>(vec, &p_, &h->deviceBytes);                           \
+        if (rc_ != RT_OK) {                                                          \
+            rt_scene_free(h);                                                        \
+            return rc_;                                                              \
+        }                                                                            \
+        h->allocations.push_back(p_);                                                \
+        h->dev.field = p_;                                                           \
+    } while (0)
+    RT_UP(nodes, packed->nodes, DevNode);
+    RT_UP(spheres, packed->spheres, DevSphere);
+    RT_UP(sphere_material, packed->sphere_material, int32_t);
+    RT_UP(moving, packed->moving, DevMovingSphere);
+    RT_UP(quads, packed->quads, DevQuad);
+    RT_UP(media, packed->media, DevMedium);
+    RT_UP(materials, packed->materials, DevMaterial);
+    RT_UP(textures, packed->textures, DevTexture);
+    RT_UP(perlins, packed->perlins, DevPerlin);
+#undef RT_UP
+    for (size_t k = 0; k < packed->image_bytes.size(); ++k) {
+        DevImage im{};
+        im.width = packed->image_w[k];
+        im.height = packed->image_h[k];
+        if (!packed->image_bytes[k].empty()) {
+            uint8_t* p = nullptr;
+            RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), packed->image_bytes[k].size()));
+            RT_CUDA(cudaMemcpy(p, packed->image_bytes[k].data(), packed->image_bytes[k].size(), cudaMemcpyHostToDevice));
+            h->allocations.push_back(p);
+            h->deviceBytes += packed->image_bytes[k].size();
+            im.rgb = p;
+        }
+        h->images.push_back(im);
+    }
+    {
+        DevImage* p = nullptr;
+        int rc = UploadVec<DevImage>(h->images, &p, &h->deviceBytes);
+        if (rc != RT_OK) {
+            rt_scene_free(h);
+            return rc;
+        }
+        h->allocations.push_back(p);
+        h->dev.images = p;
+    }
+    h->dev.root_ref = packed->root_ref;
+    h->dev.n_nodes = (int)packed->nodes.size();
+    h->dev.n_spheres = (int)packed->spheres.size();
+    h->dev.n_moving = (int)packed->moving.size();
+    h->dev.n_quads = (int)packed->quads.size();
+    h->dev.n_media = (int)packed->media.size();
+    h->dev.n_materials = (int)packed->materials.size();
+    h->dev.n_textures = (int)packed->textures.size();
+    h->dev.features = packed->features;
+
+    auto pad16 = [](size_t b) { return (uint32_t)((b + 15) / 16 * 16); };
+    h->stagedBytes = pad16(std::max<size_t>(1, packed->nodes.size()) * sizeof(DevNode)) +
+                     pad16(std::max<size_t>(1, packed->spheres.size()) * sizeof(DevSphere)) +
+                     pad16(std::max<size_t>(1, packed->sphere_material.size()) * sizeof(int32_t)) +
+                     pad16(std::max<size_t>(1, packed->moving.size()) * sizeof(DevMovingSphere)) +
+                     pad16(std::max<size_t>(1, packed->quads.size()) * sizeof(DevQuad)) +
+                     pad16(std::max<size_t>(1, packed->media.size()) * sizeof(DevMedium)) +
+                     pad16(std::max<size_t>(1, packed->materials.size()) * sizeof(DevMaterial));
+
+    RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->stats), 4 * sizeof(unsigned long long)));
+    RT_CUDA(cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long)));
+    RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->tileCounter), sizeof(unsigned int)));
+    *out = h;
+    return RT_OK;
+}
+
+int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p)
+{
+    if (!h || !cam || !p) {
+        rt_set_error("rt_render: NULL argument");
+        return RT_ERR_INVALID;
+    }
+    if (cam->image_width <= 0 || cam->image_height <= 0 || cam->max_depth <= 0 || cam->max_depth > 254 ||
+        p->sample_end < p->sample_begin || p->sample_begin < 0) {
+        rt_set_error("rt_render: bad camera or sample range (max_depth must be 1..254)");
+        return RT_ERR_INVALID;
+    }
+    if ((long long)cam->image_width * cam->image_height > 0x7fffffffLL / 3) {
+        rt_set_error("rt_render: image too large");
+        return RT_ERR_INVALID;
+    }
+    if (p->variant == RT_VARIANT_WAVEFRONT) {
+        rt_set_error("rt_render: the wavefront variant is not built in this version");
+        return RT_ERR_UNSUPPORTED;
+    }
+    RT_CUDA(cudaSetDevice(h->device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
+    const size_t nFloats = (size_t)cam->image_width * cam->image_height * 3;
+    float* accum = p->accum;
+    if (!accum) {
+        if (h->accumFloats != nFloats) {
+            if (h->accum) RT_CUDA(cudaFree(h->accum));
+            h->accum = nullptr;
+            RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->accum), nFloats * sizeof(float)));
+            h->accumFloats = nFloats;
+            RT_CUDA(cudaMemsetAsync(h->accum, 0, nFloats * sizeof(float), stream));
+        }
+        accum = h->accum;
+    }
+    if (p->clear) {
+        RT_CUDA(cudaMemsetAsync(accum, 0, nFloats * sizeof(float), stream));
+        RT_CUDA(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), stream));
+    }
+    RT_CUDA(cudaMemsetAsync(h->tileCounter, 0, sizeof(unsigned int), stream));
+
+    const DevCamera dc = rtpack::MakeCamera(*cam);
+    RenderArgs a{};
+    a.accum = accum;
+    a.stats = h->stats;
+    a.tileCounter = h->tileCounter;
+    a.sampleBegin = p->sample_begin;
+    a.sampleEnd = p->sample_end;
+    a.seed = p->seed;
+    a.tilesX = (cam->image_width + kTileW - 1) / kTileW;
+    a.tilesY = (cam->image_height + kTileH - 1) / kTileH;
+    auto pad16 = [](size_t b) { return (uint32_t)((b + 15) / 16 * 16); };
+    const rtpack::Packed& pk = *h->host;
+    a.nodesBytes = pad16(std::max<size_t>(1, pk.nodes.size()) * sizeof(DevNode));
+    a.spheresBytes = pad16(std::max<size_t>(1, pk.spheres.size()) * sizeof(DevSphere));
+    a.sphereMatBytes = pad16(std::max<size_t>(1, pk.sphere_material.size()) * sizeof(int32_t));
+    a.movingBytes = pad16(std::max<size_t>(1, pk.moving.size()) * sizeof(DevMovingSphere));
+    a.quadsBytes = pad16(std::max<size_t>(1, pk.quads.size()) * sizeof(DevQuad));
+    a.mediaBytes = pad16(std::max<size_t>(1, pk.media.size()) * sizeof(DevMedium));
+    a.materialsBytes = pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial));
+
+    int threads = p->block_threads > 0 ? p->block_threads : 512;
+    threads = std::max(32, std::min(1024, (threads / 32) * 32));
+    int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;
+    const size_t stackBytes = (size_t)threads * 4 * kStackLevels;
+    const bool wantStats = (p->flags & 0x100) != 0;
+    const bool smem = !(p->flags & 0x200) && stackBytes + h->stagedBytes <= (size_t)h->maxSmemOptin / (size_t)blocksPerSm;
+    const size_t smemBytes = stackBytes + (smem ? h->stagedBytes : 0);
+    if (smemBytes > (size_t)h->maxSmemOptin) {
+        rt_set_error("rt_render: block of %d threads needs %zu B of shared memory (max %d)", threads, smemBytes,
+                     h->maxSmemOptin);
+        return RT_ERR_INVALID;
+    }
+    KernelFn fn = PickKernelForFeatures(h->dev.features, smem, wantStats, &h->pickedFeatures);
+    RT_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    const int nTiles = a.tilesX * a.tilesY;
+    const int warpsPerBlock = threads / 32;
+    int blocks = h->smCount * blocksPerSm;
+    blocks = std::max(1, std::min(blocks, (nTiles + warpsPerBlock - 1) / warpsPerBlock));
+    h->fitsSmem = smem;
+    fn<<<blocks, threads, smemBytes, stream>>>(h->dev, dc, a);
+    RT_CUDA(cudaGetLastError());
+    h->lastStream = stream;
+    h->lastCam = *cam;
+    h->rendered = true;
+    return RT_OK;
+}
+
+int rt_accum_ptr(rt_scene_handle h, float** dev_ptr, uint64_t* n_floats)
+{
+    if (!h || !dev_ptr) {
+        rt_set_error("rt_accum_ptr: NULL argument");
+        return RT_ERR_INVALID;
+    }
+    *dev_ptr = h->accum;
+    if (n_floats) *n_floats = h->accumFloats;
+    return h->accum ? RT_OK : RT_ERR_STATE;
+}
+
+int rt_sync(rt_scene_handle h)
+{
+    if (!h) {
+        rt_set_error("rt_sync: NULL handle");
+        return RT_ERR_INVALID;
+    }
+    RT_CUDA(cudaSetDevice(h->device));
+    RT_CUDA(cudaStreamSynchronize(h->lastStream));
+    return RT_OK;
+}
+
+int rt_readback(rt_scene_handle h, const float* accum, float* linear_rgb, uint8_t* srgb8, rt_stats* stats)
+{
+    if (!h) {
+        rt_set_error("rt_readback: NULL handle");
+        return RT_ERR_INVALID;
+    }
+    if (!h->rendered) {
+        rt_set_error("rt_readback: nothing rendered yet");
+        return RT_ERR_STATE;
+    }
+    RT_CUDA(cudaSetDevice(h->device));
+    const int W = h->lastCam.image_width, H = h->lastCam.image_height;
+    const size_t nFloats = (size_t)W * H * 3;
+    const float* src = accum ? accum : h->accum;
+    if (!src) {
+        rt_set_error("rt_readback: no accumulator");
+        return RT_ERR_STATE;
+    }
+    cudaStream_t stream = h->lastStream;
+    if (linear_rgb || srgb8) {
+        if (linear_rgb && !h->linearStage) RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->linearStage), nFloats * sizeof(float)));
+        if (srgb8 && !h->srgbStage) RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->srgbStage), nFloats));
+        const int n = W * H;
+        const float invSpp = 1.0f / (float)h->lastCam.samples_per_pixel;
+        ResolveKernel<<<(n + 255) / 256, 256, 0, stream>>>(src, linear_rgb ? h->linearStage : nullptr,
+                                                           srgb8 ? h->srgbStage : nullptr, W, H, invSpp);
+        RT_CUDA(cudaGetLastError());
+        if (linear_rgb)
+            RT_CUDA(cudaMemcpyAsync(linear_rgb, h->linearStage, nFloats * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        if (srgb8) RT_CUDA(cudaMemcpyAsync(srgb8, h->srgbStage, nFloats, cudaMemcpyDeviceToHost, stream));
+    }
+    if (stats) {
+        unsigned long long s[4];
+        RT_CUDA(cudaMemcpyAsync(s, h->stats, sizeof s, cudaMemcpyDeviceToHost, stream));
+        RT_CUDA(cudaStreamSynchronize(stream));
+        stats->rays = s[0];
+        stats->paths = s[1];
+        stats->node_tests = s[2];
+        stats->prim_tests = s[3];
+    }
+    RT_CUDA(cudaStreamSynchronize(stream));
+    return RT_OK;
+}
+
+int rt_scene_free(rt_scene_handle h)
+{
+    if (!h) return RT_OK;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocations) cudaFree(p);
+    if (h->accum) cudaFree(h->accum);
+    if (h->linearStage) cudaFree(h->linearStage);
+    if (h->srgbStage) cudaFree(h->srgbStage);
+    if (h->stats) cudaFree(h->stats);
+    if (h->tileCounter) cudaFree(h->tileCounter);
+    delete h->host;
+    delete h;
+    return RT_OK;
+}
+
+int rt_scene_get_info(rt_scene_handle h, rt_scene_info* info)
+{
+    if (!h || !info) {
+        rt_set_error("rt_scene_get_info: NULL argument");
+        return RT_ERR_INVALID;
+    }
+    std::memset(info, 0, sizeof *info);
+    info->n_prims_baked = h->dev.n_spheres + h->dev.n_moving + h->dev.n_quads;
+    info->n_nodes = h->dev.n_nodes;
+    info->n_media = h->dev.n_media;
+    info->max_depth_bvh = h->host->max_depth;
+    info->features = h->dev.features;
+    info->scene_in_smem = h->fitsSmem ? 1 : 0;
+    info->device_bytes = h->deviceBytes;
+    for (int k = 0; k < 8; ++k) info->medium_visits[k] = h->host->medium_visits[k];
+    return RT_OK;
+}
+
+float rt_rng_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t domain, uint32_t dim)
+{
+    const rt_u4 b = rt_rng_block(seed, pixel, sample, slot, domain, dim >> 2);
+    return rt_bits_to_u01(rt_u4_lane(b, dim & 3u));
+}
+
+int rt_write_ppm(const char* path, const uint8_t* srgb8, int32_t width, int32_t height)
+{
+    if (!path || !srgb8 || width <= 0 || height <= 0) {
+        rt_set_error("rt_write_ppm: bad argument");
+        return RT_ERR_INVALID;
+    }
+    FILE* f = std::fopen(path, "w");
+    if (!f) {
+        rt_set_error("rt_write_ppm: cannot open %s", path);
+        return RT_ERR_INVALID;
+    }
+    // kernel.cu:697: "P3\nW H\n255\n", then "r g b\n" per pixel, top row first
+    std::fprintf(f, "P3\n%d %d\n255\n", width, height);
+    std::string buf;
+    buf.reserve(1 << 20);
+    char tmp[16];
+    const size_t n = (size_t)width * height;
+    for (size_t k = 0; k < n; ++k) {
+        const int len = std::snprintf(tmp, sizeof tmp, "%d %d %d\n", srgb8[3 * k], srgb8[3 * k + 1], srgb8[3 * k + 2]);
+        buf.append(tmp, (size_t)len);
+        if (buf.size() > (1 << 20) - 32) {
+            std::fwrite(buf.data(), 1, buf.size(), f);
+            buf.clear();
+        }
+    }
+    std::fwrite(buf.data(), 1, buf.size(), f);
+    std::fclose(f);
+    return RT_OK;
+}
+
+int rt_abi_sizeof(const char* name)
+{
+    const std::string n = name ? name : "";
+    if (n == "rt_prim") return (int)sizeof(rt_prim);
+    if (n == "rt_xform") return (int)sizeof(rt_xform);
+    if (n == "rt_object") return (int)sizeof(rt_object);
+    if (n == "rt_material") return (int)sizeof(rt_material);
+    if (n == "rt_texture") return (int)sizeof(rt_texture);
+    if (n == "rt_perlin") return (int)sizeof(rt_perlin);
+    if (n == "rt_image") return (int)sizeof(rt_image);
+    if (n == "rt_scene_desc") return (int)sizeof(rt_scene_desc);
+    if (n == "rt_camera") return (int)sizeof(rt_camera);
+    if (n == "rt_upload_options") return (int)sizeof(rt_upload_options);
+    if (n == "rt_render_params") return (int)sizeof(rt_render_params);
+    if (n == "rt_stats") return (int)sizeof(rt_stats);
+    if (n == "rt_scene_info") return (int)sizeof(rt_scene_info);
+    return -1;
+}
+
+} // extern "C"

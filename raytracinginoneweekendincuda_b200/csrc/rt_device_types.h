@@ -1,0 +1,161 @@
+// rt_device_types.h -- layout of the scene in HBM / shared memory.
+//
+// Everything the kernel reads is a flat array of 16-byte-aligned records read
+// with 128-bit loads.  World-space only: the reference's instance wrappers
+// (Translate / RotateY, reference Instance.h:28-159) are baked into the
+// primitives at upload, so the device never transforms a ray.
+//
+// Precision policy (DESIGN.md "numerics"): positions -- ray origins, sphere
+// centres, quad corners, plane offsets -- are FP64; directions, normals,
+// colours, BVH boxes and all shading are fp32.  B200 issues FP64 at half the
+// fp32 rate, which makes this affordable; it is what keeps discrete decisions
+// (hit/miss at tMin, face tests) equal to the FP64 reference.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RT_ALIGN(n) __align__(n)
+#else
+#define RT_ALIGN(n) alignas(n)
+#endif
+
+// ---- BVH node: 32 bytes = two 128-bit loads.  Children of an internal node
+// are adjacent (index c and c+1), so one step fetches 64 contiguous bytes.
+struct RT_ALIGN(16) DevNode {
+    float lo[3];
+    uint32_t ref; // what lies below this box: see RT_REF_*
+    float hi[3];
+    uint32_t aux; // unused (0); keeps the record at 32 bytes
+};
+
+// ref encoding.  Internal: index of the first of its two children.  Leaf:
+//   bit 31      = 1
+//   bits 30..29 = primitive type (RT_LEAF_*)
+//   bits 28..19 = count-1 (1..1024 primitives)
+//   bits 18..0  = first index in that type's array
+#define RT_REF_LEAF 0x80000000u
+#define RT_LEAF_SPHERE 0u
+#define RT_LEAF_MOVING 1u
+#define RT_LEAF_QUAD 2u
+#define RT_LEAF_MEDIUM 3u
+#define RT_REF_TYPE(r) (((r) >> 29) & 3u)
+#define RT_REF_COUNT(r) ((((r) >> 19) & 1023u) + 1u)
+#define RT_REF_FIRST(r) ((r)&0x7ffffu)
+#define RT_REF_MAKE_LEAF(type, first, count) \
+    (RT_REF_LEAF | ((uint32_t)(type) << 29) | (((uint32_t)(count)-1u) << 19) | (uint32_t)(first))
+#define RT_MAX_LEAF_PRIMS 1024
+#define RT_MAX_PRIMS_PER_TYPE (1 << 19)
+
+// Hit identifier carried out of traversal: type in bits 30..29, index below.
+#define RT_HIT_NONE 0xffffffffu
+#define RT_HIT_MAKE(type, index) (((uint32_t)(type) << 29) | (uint32_t)(index))
+#define RT_HIT_TYPE(h) (((h) >> 29) & 3u)
+#define RT_HIT_INDEX(h) ((h)&0x1fffffffu)
+
+// ---- Sphere (reference Sphere.h:8-21): 32 bytes, all FP64 (the quadratic's
+// b and c are formed in FP64).  The material index lives in a parallel int
+// array that is read once per ray, after traversal.
+struct RT_ALIGN(16) DevSphere {
+    double cx, cy, cz;
+    double radius;
+};
+
+// ---- MovingSphere (reference MovingSphere.h:20-36): 64 bytes.
+// centre(time) = c0 + ((time - time0) * inv_dt) * dc, dc = c1 - c0.
+struct RT_ALIGN(16) DevMovingSphere {
+    double c0x, c0y, c0z;
+    float radius;
+    int32_t material;
+    double dcx, dcy, dcz;
+    float time0;
+    float inv_dt; // 1/(time1-time0)
+};
+
+// ---- Quad (reference Quad.h:25-37): 96 bytes.  Plane (n, D) in FP64 so that
+// t = (D - n.O)/(n.d) does not lose the origin's position on the plane.
+struct RT_ALIGN(16) DevQuad {
+    double qx, qy, qz;
+    double D;
+    double nx, ny, nz;
+    float wx, wy, wz;
+    float ux, uy, uz;
+    float vx, vy, vz;
+    int32_t material;
+};
+
+// ---- ConstantMedium (reference ConstantMedium.h:18-50): 32 bytes.
+struct RT_ALIGN(16) DevMedium {
+    uint32_t boundary_ref;  // leaf-style ref to the boundary primitives
+    int32_t phase_material; // its Isotropic
+    float neg_inv_density;  // -1/rho
+    int32_t medium_id;      // keys the RNG domain
+    int32_t visits;         // reference-topology visit multiplicity (SURVEY trap T2)
+    int32_t _p[3];
+};
+
+// ---- Material: 32 bytes.
+struct RT_ALIGN(16) DevMaterial {
+    float r, g, b; // metal albedo, or the colour when `texture` < 0 (solid folded in)
+    float param;   // metal fuzz | dielectric index of refraction
+    int32_t type;  // RT_MAT_*
+    int32_t texture;
+    int32_t _p[2];
+};
+
+// ---- Texture: 48 bytes.
+struct RT_ALIGN(16) DevTexture {
+    int32_t type; // RT_TEX_*
+    int32_t even, odd;
+    int32_t index; // image or perlin index
+    float r, g, b;
+    float scale;      // noise scale
+    double inv_scale; // checker 1/scale (Texture.h:65)
+    double _p;
+};
+
+// ---- Perlin tables (reference Perlin.h:22-34): 256 float4 vectors + 3x256 bytes.
+struct RT_ALIGN(16) DevPerlin {
+    float ranvec[256][4];
+    uint8_t perm_x[256];
+    uint8_t perm_y[256];
+    uint8_t perm_z[256];
+    uint8_t _p[256];
+};
+
+struct DevImage {
+    const uint8_t* rgb;
+    int32_t width, height;
+};
+
+// Scene feature bits: select the kernel instantiation.
+#define RT_FEAT_MOVING 1
+#define RT_FEAT_QUAD 2
+#define RT_FEAT_MEDIUM 4
+#define RT_FEAT_TEXTURE 8 /* any non-solid texture */
+
+struct DevScene {
+    const DevNode* nodes;
+    const DevSphere* spheres;
+    const int32_t* sphere_material;
+    const DevMovingSphere* moving;
+    const DevQuad* quads;
+    const DevMedium* media;
+    const DevMaterial* materials;
+    const DevTexture* textures;
+    const DevPerlin* perlins;
+    const DevImage* images;
+    uint32_t root_ref;
+    int32_t n_nodes, n_spheres, n_moving, n_quads, n_media, n_materials, n_textures;
+    int32_t features;
+};
+
+// Camera frame (reference Camera.h:36-71), FP64 as computed on the host.
+struct DevCamera {
+    double origin[3], llc[3], horiz[3], vert[3];
+    double u[3], v[3];
+    double lens_radius;
+    float time0, time1;
+    float background[3];
+    int32_t width, height, max_depth;
+};

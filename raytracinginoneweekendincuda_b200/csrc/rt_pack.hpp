@@ -1,0 +1,810 @@
+// rt_pack.hpp -- host side of rt_scene_upload: bake, build the BVH, pack.
+//
+// Input is the flat FP64 scene description of include/rt_abi.h (the
+// reference's object graph as its constructors leave it).  Output is the
+// device layout of rt_device_types.h:
+//   1. instances are baked: every primitive is moved to world space through
+//      its Translate/RotateY chain (reference Instance.h:41-56,116-150 run the
+//      other way round: they move the ray into object space per test);
+//   2. a BVH is built over the baked primitives -- binned SAH by default, the
+//      reference's median-split topology (BvhNode.h:50-90) or a plain list
+//      (the reference's BVH==list cross-check) on request;
+//   3. primitives are re-ordered so each leaf is a contiguous run of one type.
+// Host only, no CUDA.
+#pragma once
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_abi.h"
+#include "rt_device_types.h"
+
+namespace rtpack {
+
+struct Box3 {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
+    double hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    void Grow(const double* p)
+    {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], p[a]);
+            hi[a] = std::max(hi[a], p[a]);
+        }
+    }
+    void Grow(const Box3& b)
+    {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], b.lo[a]);
+            hi[a] = std::max(hi[a], b.hi[a]);
+        }
+    }
+    double Area() const
+    {
+        const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.0;
+        return 2.0 * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+// A baked primitive, still FP64, with its world box.
+struct Baked {
+    int type;     // RT_LEAF_SPHERE / MOVING / QUAD
+    int material;
+    double a[3], b[3], c[3]; // sphere: centre | moving: c0, c1 | quad: Q, u, v
+    double radius, time0, time1;
+    Box3 box;
+};
+
+// Something the BVH treats as one leaf entry.
+struct Item {
+    int type;  // RT_LEAF_*
+    int index; // SAH: index into baked[] (or media[] for RT_LEAF_MEDIUM)
+    int first, count; // REFERENCE/LIST: run of baked prims (all of `type`)
+    Box3 box;
+};
+
+struct BuildNode {
+    Box3 box;
+    int left = -1, right = -1;    // children (BuildNode indices) or -1
+    std::vector<int> items;       // leaf: item indices (same type)
+};
+
+struct Packed {
+    std::vector<DevNode> nodes;
+    std::vector<DevSphere> spheres;
+    std::vector<int32_t> sphere_material; // parallel to spheres: read once per ray, after traversal
+    std::vector<DevMovingSphere> moving;
+    std::vector<DevQuad> quads;
+    std::vector<DevMedium> media;
+    std::vector<DevMaterial> materials;
+    std::vector<DevTexture> textures;
+    std::vector<DevPerlin> perlins;
+    std::vector<std::vector<uint8_t>> image_bytes;
+    std::vector<int32_t> image_w, image_h;
+    uint32_t root_ref = 0;
+    int features = 0;
+    int max_depth = 0;
+    int medium_visits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n_media = 0;
+};
+
+inline void ApplyChainPoint(const rt_scene_desc& d, const rt_prim& p, double* v, bool isPoint)
+{
+    // object -> world: innermost wrapper first (chain is stored outermost first)
+    for (int k = p.xform_count - 1; k >= 0; --k) {
+        const rt_xform& x = d.xforms[p.first_xform + k];
+        if (x.type == RT_XFORM_TRANSLATE) {
+            if (isPoint)
+                for (int a = 0; a < 3; ++a) v[a] += x.v[a];
+        } else {
+            // Instance.h:136-147: x = c x' + s z', z = -s x' + c z'
+            const double s = x.v[0], c = x.v[1];
+            const double nx = c * v[0] + s * v[2];
+            const double nz = -s * v[0] + c * v[2];
+            v[0] = nx;
+            v[2] = nz;
+        }
+    }
+}
+
+inline Baked Bake(const rt_scene_desc& d, const rt_prim& p)
+{
+    Baked b;
+    std::memset(&b, 0, sizeof b);
+    b.box = Box3();
+    b.material = p.material;
+    b.radius = p.radius;
+    b.time0 = p.time0;
+    b.time1 = p.time1;
+    for (int a = 0; a < 3; ++a) {
+        b.a[a] = p.a[a];
+        b.b[a] = p.b[a];
+        b.c[a] = p.c[a];
+    }
+    if (p.type == RT_PRIM_SPHERE) {
+        b.type = RT_LEAF_SPHERE;
+        ApplyChainPoint(d, p, b.a, true);
+        for (int a = 0; a < 3; ++a) {
+            b.box.lo[a] = b.a[a] - p.radius;
+            b.box.hi[a] = b.a[a] + p.radius;
+        }
+    } else if (p.type == RT_PRIM_MOVING_SPHERE) {
+        b.type = RT_LEAF_MOVING;
+        ApplyChainPoint(d, p, b.a, true);
+        ApplyChainPoint(d, p, b.b, true);
+        for (int a = 0; a < 3; ++a) {
+            b.box.lo[a] = std::min(b.a[a], b.b[a]) - p.radius;
+            b.box.hi[a] = std::max(b.a[a], b.b[a]) + p.radius;
+        }
+    } else if (p.type == RT_PRIM_QUAD) {
+        b.type = RT_LEAF_QUAD;
+        ApplyChainPoint(d, p, b.a, true);
+        ApplyChainPoint(d, p, b.b, false);
+        ApplyChainPoint(d, p, b.c, false);
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) {
+                double corner[3];
+                for (int a = 0; a < 3; ++a) corner[a] = b.a[a] + i * b.b[a] + j * b.c[a];
+                b.box.Grow(corner);
+            }
+    } else {
+        throw std::invalid_argument("unknown primitive type");
+    }
+    return b;
+}
+
+// ---------------------------------------------------------------- builders
+struct Builder {
+    std::vector<Item> items;
+    std::vector<BuildNode> nodes;
+    int maxLeaf = 2;
+    int maxDepth = 0;
+
+    static double IsectCost(int type)
+    {
+        switch (type) {
+        case RT_LEAF_SPHERE: return 1.5;
+        case RT_LEAF_MOVING: return 1.8;
+        case RT_LEAF_QUAD: return 1.3;
+        default: return 12.0;
+        }
+    }
+
+    int NewLeaf(const std::vector<int>& ids, const Box3& box)
+    {
+        // a leaf holds one primitive type, and a medium is always a leaf of its
+        // own; mixed sets are chained through internal nodes sharing `box`
+        std::vector<std::vector<int>> groups;
+        for (int t = 0; t < 3; ++t) {
+            std::vector<int> g;
+            for (int id : ids)
+                if (items[id].type == t) g.push_back(id);
+            if (!g.empty()) groups.push_back(g);
+        }
+        for (int id : ids)
+            if (items[id].type == RT_LEAF_MEDIUM) groups.push_back(std::vector<int>(1, id));
+        int made = -1;
+        for (const std::vector<int>& g : groups) {
+            BuildNode leaf;
+            leaf.box = Box3();
+            for (int id : g) leaf.box.Grow(items[id].box);
+            leaf.items = g;
+            nodes.push_back(leaf);
+            const int me = (int)nodes.size() - 1;
+            if (made < 0) {
+                made = me;
+            } else {
+                BuildNode join;
+                join.box = box;
+                join.left = made;
+                join.right = me;
+                nodes.push_back(join);
+                made = (int)nodes.size() - 1;
+            }
+        }
+        return made;
+    }
+
+    // Binned SAH, 16 bins, all three axes.
+    int BuildSah(std::vector<int>& ids, int depth)
+    {
+        maxDepth = std::max(maxDepth, depth);
+        Box3 box, cbox;
+        for (int id : ids) {
+            box.Grow(items[id].box);
+            double c[3];
+            for (int a = 0; a < 3; ++a) c[a] = 0.5 * (items[id].box.lo[a] + items[id].box.hi[a]);
+            cbox.Grow(c);
+        }
+        const int n = (int)ids.size();
+        if (n == 1) return NewLeaf(ids, box);
+
+        double leafCost = 0.0;
+        for (int id : ids) leafCost += IsectCost(items[id].type);
+
+        const int kBins = 16;
+        double bestCost = DBL_MAX;
+        int bestAxis = -1, bestBin = -1;
+        const double invArea = box.Area() > 0 ? 1.0 / box.Area() : 0.0;
+        for (int axis = 0; axis < 3; ++axis) {
+            const double ext = cbox.hi[axis] - cbox.lo[axis];
+            if (!(ext > 0)) continue;
+            Box3 bb[kBins];
+            double bc[kBins];
+            int bn[kBins];
+            for (int k = 0; k < kBins; ++k) {
+                bc[k] = 0;
+                bn[k] = 0;
+            }
+            for (int id : ids) {
+                const double c = 0.5 * (items[id].box.lo[axis] + items[id].box.hi[axis]);
+                int k = (int)(kBins * (c - cbox.lo[axis]) / ext);
+                k = std::min(std::max(k, 0), kBins - 1);
+                bb[k].Grow(items[id].box);
+                bc[k] += IsectCost(items[id].type);
+                bn[k]++;
+            }
+            double rightArea[kBins], rightCost[kBins];
+            Box3 acc;
+            double cacc = 0;
+            for (int k = kBins - 1; k > 0; --k) {
+                acc.Grow(bb[k]);
+                cacc += bc[k];
+                rightArea[k] = acc.Area();
+                rightCost[k] = cacc;
+            }
+            acc = Box3();
+            cacc = 0;
+            int nl = 0;
+            for (int k = 0; k < kBins - 1; ++k) {
+                acc.Grow(bb[k]);
+                cacc += bc[k];
+                nl += bn[k];
+                if (nl == 0 || nl == n) continue;
+                const double cost = 1.0 + invArea * (acc.Area() * cacc + rightArea[k + 1] * rightCost[k + 1]);
+                if (cost < bestCost) {
+                    bestCost = cost;
+                    bestAxis = axis;
+                    bestBin = k;
+                }
+            }
+        }
+        const bool depthLeft = depth + (int)std::ceil(std::log2((double)std::max(n, 2))) < 26;
+        if (n <= maxLeaf && (bestAxis < 0 || leafCost <= bestCost)) return NewLeaf(ids, box);
+
+        std::vector<int> L, R;
+        if (bestAxis >= 0 && depthLeft) {
+            const double ext = cbox.hi[bestAxis] - cbox.lo[bestAxis];
+            for (int id : ids) {
+                const double c = 0.5 * (items[id].box.lo[bestAxis] + items[id].box.hi[bestAxis]);
+                int k = (int)(kBins * (c - cbox.lo[bestAxis]) / ext);
+                k = std::min(std::max(k, 0), kBins - 1);
+                (k <= bestBin ? L : R).push_back(id);
+            }
+        }
+        if (L.empty() || R.empty()) {
+            // degenerate (coincident centroids) or depth budget: median split on the widest axis
+            int axis = 0;
+            for (int a = 1; a < 3; ++a)
+                if (box.hi[a] - box.lo[a] > box.hi[axis] - box.lo[axis]) axis = a;
+            std::vector<int> sorted = ids;
+            std::stable_sort(sorted.begin(), sorted.end(), [&](int x, int y) {
+                return items[x].box.lo[axis] + items[x].box.hi[axis] < items[y].box.lo[axis] + items[y].box.hi[axis];
+            });
+            L.assign(sorted.begin(), sorted.begin() + n / 2);
+            R.assign(sorted.begin() + n / 2, sorted.end());
+        }
+        const int l = BuildSah(L, depth + 1);
+        const int r = BuildSah(R, depth + 1);
+        BuildNode in;
+        in.box = box;
+        in.left = l;
+        in.right = r;
+        nodes.push_back(in);
+        return (int)nodes.size() - 1;
+    }
+
+    // BvhNode.h:50-90 on item order: longest axis of the union box (ties fall
+    // towards Z, AABB.h:101-107), stable insertion sort on box-min with strict
+    // `<` (BvhNode.h:170-193), midpoint split.  visits[i] counts how often item
+    // i is referenced (span-1 nodes reference their leaf twice).
+    int BuildReference(std::vector<int>& order, int start, int end, int depth, std::vector<int>& visits)
+    {
+        maxDepth = std::max(maxDepth, depth);
+        Box3 box;
+        for (int i = start; i < end; ++i) box.Grow(items[order[i]].box);
+        const double sx = box.hi[0] - box.lo[0], sy = box.hi[1] - box.lo[1], sz = box.hi[2] - box.lo[2];
+        const int axis = (sx > sy) ? (sx > sz ? 0 : 2) : (sy > sz ? 1 : 2);
+        const int span = end - start;
+        if (span == 1) {
+            visits[order[start]] += 2;
+            std::vector<int> one(1, order[start]);
+            return NewLeaf(one, box);
+        }
+        int l, r;
+        if (span == 2) {
+            visits[order[start]] += 1;
+            visits[order[start + 1]] += 1;
+            std::vector<int> a(1, order[start]), b(1, order[start + 1]);
+            l = NewLeaf(a, items[order[start]].box);
+            r = NewLeaf(b, items[order[start + 1]].box);
+        } else {
+            for (int i = start + 1; i < end; ++i) {
+                const int key = order[i];
+                const double keyMin = items[key].box.lo[axis];
+                int j = i - 1;
+                while (j >= start && keyMin < items[order[j]].box.lo[axis]) {
+                    order[j + 1] = order[j];
+                    --j;
+                }
+                order[j + 1] = key;
+            }
+            const int mid = start + span / 2;
+            l = BuildReference(order, start, mid, depth + 1, visits);
+            r = BuildReference(order, mid, end, depth + 1, visits);
+        }
+        BuildNode in;
+        in.box = box;
+        in.left = l;
+        in.right = r;
+        nodes.push_back(in);
+        return (int)nodes.size() - 1;
+    }
+
+    // Plain list: a right-deep chain whose boxes are all the scene box.
+    int BuildList()
+    {
+        Box3 box;
+        for (const Item& it : items) box.Grow(it.box);
+        int chain = -1;
+        for (int i = (int)items.size() - 1; i >= 0; --i) {
+            std::vector<int> one(1, i);
+            const int leaf = NewLeaf(one, box);
+            nodes[leaf].box = box;
+            if (chain < 0) {
+                chain = leaf;
+            } else {
+                BuildNode in;
+                in.box = box;
+                in.left = leaf;
+                in.right = chain;
+                nodes.push_back(in);
+                chain = (int)nodes.size() - 1;
+            }
+        }
+        maxDepth = (int)items.size();
+        return chain;
+    }
+};
+
+inline float RoundDown(double v)
+{
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+inline float RoundUp(double v)
+{
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+// fp32 box that contains the FP64 box with a little slack for the fp32 slab test.
+inline void PackBox(const Box3& b, DevNode& n)
+{
+    for (int a = 0; a < 3; ++a) {
+        const double mag = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a]));
+        const double pad = 4e-7 * mag + 1e-7 * (b.hi[a] - b.lo[a]) + 1e-30;
+        n.lo[a] = RoundDown(b.lo[a] - pad);
+        n.hi[a] = RoundUp(b.hi[a] + pad);
+    }
+}
+
+struct Packer {
+    const rt_scene_desc& d;
+    const rt_upload_options& opt;
+    Packed out;
+    std::vector<Baked> baked;         // surfaces first, then medium boundaries
+    std::vector<int> bakedOfPrim;     // desc prim index -> baked index
+
+    Packer(const rt_scene_desc& desc, const rt_upload_options& o) : d(desc), opt(o) {}
+
+    void PushSphere(const Baked& b)
+    {
+        DevSphere s;
+        s.cx = b.a[0];
+        s.cy = b.a[1];
+        s.cz = b.a[2];
+        s.radius = b.radius;
+        out.spheres.push_back(s);
+        out.sphere_material.push_back(b.material);
+    }
+    void PushMoving(const Baked& b)
+    {
+        DevMovingSphere s;
+        s.c0x = b.a[0];
+        s.c0y = b.a[1];
+        s.c0z = b.a[2];
+        s.radius = (float)b.radius;
+        s.material = b.material;
+        s.dcx = b.b[0] - b.a[0];
+        s.dcy = b.b[1] - b.a[1];
+        s.dcz = b.b[2] - b.a[2];
+        s.time0 = (float)b.time0;
+        s.inv_dt = (float)(1.0 / (b.time1 - b.time0));
+        out.moving.push_back(s);
+    }
+    void PushQuad(const Baked& b)
+    {
+        // Quad.h:31-36 on the baked Q, u, v
+        const double* u = b.b;
+        const double* v = b.c;
+        const double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+        const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        const double len = std::sqrt(nn);
+        DevQuad q;
+        std::memset(&q, 0, sizeof q);
+        q.qx = b.a[0];
+        q.qy = b.a[1];
+        q.qz = b.a[2];
+        q.nx = n[0] / len;
+        q.ny = n[1] / len;
+        q.nz = n[2] / len;
+        q.D = q.nx * b.a[0] + q.ny * b.a[1] + q.nz * b.a[2];
+        q.wx = (float)(n[0] / nn);
+        q.wy = (float)(n[1] / nn);
+        q.wz = (float)(n[2] / nn);
+        q.ux = (float)u[0];
+        q.uy = (float)u[1];
+        q.uz = (float)u[2];
+        q.vx = (float)v[0];
+        q.vy = (float)v[1];
+        q.vz = (float)v[2];
+        q.material = b.material;
+        out.quads.push_back(q);
+    }
+
+    // Appends baked prims [ids] (one type) to the device arrays; returns a leaf ref.
+    uint32_t EmitRun(int type, const std::vector<int>& ids)
+    {
+        if (ids.empty() || (int)ids.size() > RT_MAX_LEAF_PRIMS) throw std::invalid_argument("leaf size out of range");
+        size_t first = 0;
+        if (type == RT_LEAF_SPHERE) {
+            first = out.spheres.size();
+            for (int i : ids) PushSphere(baked[i]);
+        } else if (type == RT_LEAF_MOVING) {
+            first = out.moving.size();
+            for (int i : ids) PushMoving(baked[i]);
+        } else {
+            first = out.quads.size();
+            for (int i : ids) PushQuad(baked[i]);
+        }
+        if (first + ids.size() > (size_t)RT_MAX_PRIMS_PER_TYPE) throw std::invalid_argument("too many primitives");
+        return RT_REF_MAKE_LEAF(type, first, ids.size());
+    }
+
+    void PackMaterials()
+    {
+        for (int i = 0; i < d.n_textures; ++i) {
+            const rt_texture& t = d.textures[i];
+            DevTexture x;
+            std::memset(&x, 0, sizeof x);
+            x.type = t.type;
+            x.even = t.even;
+            x.odd = t.odd;
+            x.index = t.type == RT_TEX_IMAGE ? t.image : t.perlin;
+            x.r = (float)t.color[0];
+            x.g = (float)t.color[1];
+            x.b = (float)t.color[2];
+            x.scale = (float)t.scale;
+            x.inv_scale = t.type == RT_TEX_CHECKER ? 1.0 / t.scale : 0.0;
+            if (t.type == RT_TEX_CHECKER && (t.even < 0 || t.even >= d.n_textures || t.odd < 0 || t.odd >= d.n_textures))
+                throw std::invalid_argument("checker texture child out of range");
+            if (t.type == RT_TEX_NOISE && (t.perlin < 0 || t.perlin >= d.n_perlins))
+                throw std::invalid_argument("noise texture perlin out of range");
+            if (t.type == RT_TEX_IMAGE && t.image >= d.n_images) throw std::invalid_argument("image index out of range");
+            out.textures.push_back(x);
+        }
+        for (int i = 0; i < d.n_materials; ++i) {
+            const rt_material& m = d.materials[i];
+            DevMaterial x;
+            std::memset(&x, 0, sizeof x);
+            x.type = m.type;
+            x.texture = -1;
+            if (m.type == RT_MAT_METAL) {
+                x.r = (float)m.albedo[0];
+                x.g = (float)m.albedo[1];
+                x.b = (float)m.albedo[2];
+                x.param = (float)m.fuzz;
+            } else if (m.type == RT_MAT_DIELECTRIC) {
+                x.param = (float)m.ior;
+            } else {
+                if (m.texture < 0 || m.texture >= d.n_textures) throw std::invalid_argument("material texture out of range");
+                const rt_texture& t = d.textures[m.texture];
+                if (t.type == RT_TEX_SOLID) {
+                    x.r = (float)t.color[0];
+                    x.g = (float)t.color[1];
+                    x.b = (float)t.color[2];
+                } else {
+                    x.texture = m.texture;
+                    out.features |= RT_FEAT_TEXTURE;
+                }
+            }
+            out.materials.push_back(x);
+        }
+        for (int i = 0; i < d.n_perlins; ++i) {
+            const rt_perlin& p = d.perlins[i];
+            DevPerlin x;
+            std::memset(&x, 0, sizeof x);
+            for (int k = 0; k < 256; ++k) {
+                for (int a = 0; a < 3; ++a) x.ranvec[k][a] = (float)p.ranvec[k][a];
+                x.perm_x[k] = (uint8_t)p.perm_x[k];
+                x.perm_y[k] = (uint8_t)p.perm_y[k];
+                x.perm_z[k] = (uint8_t)p.perm_z[k];
+            }
+            out.perlins.push_back(x);
+        }
+        for (int i = 0; i < d.n_images; ++i) {
+            const rt_image& im = d.images[i];
+            out.image_w.push_back(im.rgb ? im.width : 0);
+            out.image_h.push_back(im.rgb ? im.height : 0);
+            if (im.rgb && im.width > 0 && im.height > 0)
+                out.image_bytes.emplace_back(im.rgb, im.rgb + (size_t)im.width * im.height * 3);
+            else
+                out.image_bytes.emplace_back();
+        }
+    }
+
+    void Run()
+    {
+        if (d.abi_version != RT_ABI_VERSION) throw std::invalid_argument("rt_scene_desc.abi_version mismatch");
+        if (d.n_objects <= 0 || d.n_prims <= 0) throw std::invalid_argument("empty scene");
+        for (int i = 0; i < d.n_prims; ++i) {
+            const rt_prim& p = d.prims[i];
+            if (p.material < 0 || p.material >= d.n_materials) throw std::invalid_argument("prim material out of range");
+            if (p.xform_count < 0 || p.first_xform < 0 || p.first_xform + p.xform_count > d.n_xforms)
+                throw std::invalid_argument("prim xform chain out of range");
+        }
+        PackMaterials();
+
+        // bake everything
+        baked.reserve(d.n_prims);
+        for (int i = 0; i < d.n_prims; ++i) {
+            baked.push_back(Bake(d, d.prims[i]));
+            if (baked.back().type == RT_LEAF_MOVING) out.features |= RT_FEAT_MOVING;
+            if (baked.back().type == RT_LEAF_QUAD) out.features |= RT_FEAT_QUAD;
+        }
+
+        // media: boundary prims go straight to the device arrays (not in the BVH)
+        struct Med {
+            int object;
+            Box3 box;
+        };
+        std::vector<Med> meds;
+        for (int o = 0; o < d.n_objects; ++o) {
+            const rt_object& ob = d.objects[o];
+            if (ob.first_prim < 0 || ob.prim_count <= 0 || ob.first_prim + ob.prim_count > d.n_prims)
+                throw std::invalid_argument("object prim range out of range");
+            if (ob.kind != RT_OBJ_MEDIUM) continue;
+            if (ob.medium_id < 0 || ob.medium_id >= 8) throw std::invalid_argument("at most 8 media are supported");
+            if (ob.phase_material < 0 || ob.phase_material >= d.n_materials)
+                throw std::invalid_argument("medium phase material out of range");
+            out.features |= RT_FEAT_MEDIUM;
+            const int type = baked[ob.first_prim].type;
+            std::vector<int> ids;
+            Med m;
+            m.object = o;
+            for (int k = 0; k < ob.prim_count; ++k) {
+                if (baked[ob.first_prim + k].type != type)
+                    throw std::invalid_argument("medium boundary must be primitives of one type");
+                ids.push_back(ob.first_prim + k);
+                m.box.Grow(baked[ob.first_prim + k].box);
+            }
+            DevMedium dm;
+            std::memset(&dm, 0, sizeof dm);
+            dm.boundary_ref = EmitRun(type, ids);
+            dm.phase_material = ob.phase_material;
+            dm.neg_inv_density = (float)(-1.0 / ob.density);
+            dm.medium_id = ob.medium_id;
+            dm.visits = 1;
+            out.media.push_back(dm);
+            meds.push_back(m);
+        }
+        out.n_media = (int)meds.size();
+
+        // T2: visit multiplicity per medium from the reference topology over objects
+        {
+            Builder rb;
+            for (int o = 0; o < d.n_objects; ++o) {
+                Item it;
+                it.type = d.objects[o].kind == RT_OBJ_MEDIUM ? RT_LEAF_MEDIUM : RT_LEAF_SPHERE;
+                it.index = o;
+                it.first = it.count = 0;
+                for (int a = 0; a < 3; ++a) {
+                    it.box.lo[a] = d.objects[o].bbox[2 * a];
+                    it.box.hi[a] = d.objects[o].bbox[2 * a + 1];
+                }
+                rb.items.push_back(it);
+            }
+            std::vector<int> order(d.n_objects), visits(d.n_objects, 0);
+            for (int i = 0; i < d.n_objects; ++i) order[i] = i;
+            rb.BuildReference(order, 0, d.n_objects, 0, visits);
+            for (size_t k = 0; k < meds.size(); ++k) {
+                out.media[k].visits = visits[meds[k].object];
+                out.medium_visits[d.objects[meds[k].object].medium_id] = visits[meds[k].object];
+            }
+        }
+
+        // BVH items
+        Builder b;
+        b.maxLeaf = opt.max_leaf_prims > 0 ? std::min(opt.max_leaf_prims, 8) : 2;
+        const bool perObject = opt.bvh == RT_BVH_REFERENCE || opt.bvh == RT_BVH_NONE;
+        std::vector<std::vector<int>> runOfItem; // perObject: baked ids behind each item
+        int medIdx = 0;
+        for (int o = 0; o < d.n_objects; ++o) {
+            const rt_object& ob = d.objects[o];
+            if (ob.kind == RT_OBJ_MEDIUM) {
+                Item it;
+                it.type = RT_LEAF_MEDIUM;
+                it.index = medIdx;
+                it.first = it.count = 0;
+                it.box = meds[medIdx].box;
+                if (perObject)
+                    for (int a = 0; a < 3; ++a) {
+                        it.box.lo[a] = ob.bbox[2 * a];
+                        it.box.hi[a] = ob.bbox[2 * a + 1];
+                    }
+                b.items.push_back(it);
+                runOfItem.emplace_back();
+                ++medIdx;
+                continue;
+            }
+            if (!perObject) {
+                for (int k = 0; k < ob.prim_count; ++k) {
+                    Item it;
+                    it.type = baked[ob.first_prim + k].type;
+                    it.index = ob.first_prim + k;
+                    it.first = it.count = 0;
+                    it.box = baked[ob.first_prim + k].box;
+                    b.items.push_back(it);
+                    runOfItem.emplace_back(1, ob.first_prim + k);
+                }
+            } else {
+                // one item per object; split only where the type changes or the run exceeds a leaf
+                int k = 0;
+                bool firstPiece = true;
+                while (k < ob.prim_count) {
+                    const int type = baked[ob.first_prim + k].type;
+                    std::vector<int> ids;
+                    while (k < ob.prim_count && baked[ob.first_prim + k].type == type && (int)ids.size() < RT_MAX_LEAF_PRIMS)
+                        ids.push_back(ob.first_prim + k++);
+                    Item it;
+                    it.type = type;
+                    it.index = o;
+                    it.first = it.count = 0;
+                    for (int a = 0; a < 3; ++a) {
+                        it.box.lo[a] = ob.bbox[2 * a];
+                        it.box.hi[a] = ob.bbox[2 * a + 1];
+                    }
+                    if (!firstPiece && opt.bvh == RT_BVH_REFERENCE)
+                        throw std::invalid_argument("reference BVH mode needs single-type objects of <= 1024 primitives");
+                    firstPiece = false;
+                    b.items.push_back(it);
+                    runOfItem.push_back(ids);
+                }
+            }
+        }
+        if (b.items.empty()) throw std::invalid_argument("scene has no primitives");
+
+        int root;
+        if (opt.bvh == RT_BVH_NONE) {
+            root = b.BuildList();
+        } else if (opt.bvh == RT_BVH_REFERENCE) {
+            std::vector<int> order(b.items.size()), visits(b.items.size(), 0);
+            for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+            root = b.BuildReference(order, 0, (int)order.size(), 0, visits);
+        } else {
+            std::vector<int> ids(b.items.size());
+            for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i;
+            root = b.BuildSah(ids, 0);
+        }
+        out.max_depth = b.maxDepth;
+        if (opt.bvh != RT_BVH_NONE && b.maxDepth > 30) throw std::invalid_argument("BVH deeper than the traversal stack");
+
+        // flatten: node 0 = root record, node 1 = pad, children pairs at even indices
+        auto leafRef = [&](const BuildNode& n) -> uint32_t {
+            const int type = b.items[n.items[0]].type;
+            if (type == RT_LEAF_MEDIUM) {
+                if (n.items.size() != 1) {
+                    // several media in one leaf cannot be expressed as one run unless adjacent; keep it simple
+                    throw std::invalid_argument("internal: multi-medium leaf");
+                }
+                return RT_REF_MAKE_LEAF(RT_LEAF_MEDIUM, b.items[n.items[0]].index, 1);
+            }
+            std::vector<int> ids;
+            for (int it : n.items)
+                for (int id : runOfItem[it]) ids.push_back(id);
+            return EmitRun(type, ids);
+        };
+        out.nodes.clear();
+        out.nodes.resize(2);
+        std::memset(out.nodes.data(), 0, 2 * sizeof(DevNode));
+        // iterative DFS; each entry = (build node, slot it occupies)
+        struct Todo {
+            int node, slot;
+        };
+        std::vector<Todo> stack;
+        stack.push_back(Todo{root, 0});
+        while (!stack.empty()) {
+            const Todo t = stack.back();
+            stack.pop_back();
+            const BuildNode& bn = b.nodes[t.node];
+            PackBox(bn.box, out.nodes[t.slot]);
+            out.nodes[t.slot].aux = 0;
+            if (bn.left < 0) {
+                out.nodes[t.slot].ref = leafRef(bn);
+            } else {
+                const int pair = (int)out.nodes.size();
+                out.nodes.resize(out.nodes.size() + 2);
+                out.nodes[t.slot].ref = (uint32_t)pair;
+                stack.push_back(Todo{bn.right, pair + 1});
+                stack.push_back(Todo{bn.left, pair}); // left is laid out (and its leaves emitted) first
+            }
+        }
+        out.root_ref = out.nodes[0].ref;
+    }
+};
+
+// Camera.h:36-71 in FP64.
+inline DevCamera MakeCamera(const rt_camera& c)
+{
+    DevCamera k;
+    std::memset(&k, 0, sizeof k);
+    const double aspect = double(c.image_width) / double(c.image_height);
+    double aperture = c.aperture;
+    if (aperture < 0.0) aperture = 2.0 * c.focus_dist * std::tan(c.defocus_angle * 3.14159265358979323846 / 360.0);
+    const double theta = c.vfov * 3.14159265358979323846 / 180.0;
+    const double halfHeight = std::tan(theta / 2.0);
+    const double halfWidth = aspect * halfHeight;
+    double w[3], u[3], v[3];
+    double len = 0;
+    for (int a = 0; a < 3; ++a) {
+        w[a] = c.lookfrom[a] - c.lookat[a];
+        len += w[a] * w[a];
+    }
+    len = std::sqrt(len);
+    for (int a = 0; a < 3; ++a) w[a] = (1 / len) * w[a];
+    u[0] = c.vup[1] * w[2] - c.vup[2] * w[1];
+    u[1] = c.vup[2] * w[0] - c.vup[0] * w[2];
+    u[2] = c.vup[0] * w[1] - c.vup[1] * w[0];
+    len = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    for (int a = 0; a < 3; ++a) u[a] = (1 / len) * u[a];
+    v[0] = w[1] * u[2] - w[2] * u[1];
+    v[1] = w[2] * u[0] - w[0] * u[2];
+    v[2] = w[0] * u[1] - w[1] * u[0];
+    const double fd = c.focus_dist;
+    for (int a = 0; a < 3; ++a) {
+        k.origin[a] = c.lookfrom[a];
+        k.llc[a] = c.lookfrom[a] - halfWidth * fd * u[a] - halfHeight * fd * v[a] - fd * w[a];
+        k.horiz[a] = 2.0 * halfWidth * fd * u[a];
+        k.vert[a] = 2.0 * halfHeight * fd * v[a];
+        k.u[a] = u[a];
+        k.v[a] = v[a];
+        k.background[a] = (float)c.background[a];
+    }
+    k.lens_radius = aperture / 2.0;
+    k.time0 = (float)c.time0;
+    k.time1 = (float)c.time1;
+    k.width = c.image_width;
+    k.height = c.image_height;
+    k.max_depth = c.max_depth;
+    return k;
+}
+
+} // namespace rtpack

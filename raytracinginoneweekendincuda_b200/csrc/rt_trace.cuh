@@ -1,0 +1,683 @@
+// rt_trace.cuh -- device functions of the render path: traversal,
+// intersection, hit finalisation, textures, scattering.
+//
+// Follows the algorithm of the reference's Render -> RayColor -> BvhNode::Hit /
+// Material::Scatter (reference kernel.cu:65-154 and the class headers cited at
+// each function) over the flat device layout of rt_device_types.h.  Written
+// for sm_100a: 128-bit loads (LDS.128 when the scene is staged in shared
+// memory, LDG.E.128 through the read-only path otherwise), a per-thread
+// traversal stack in shared memory laid out [level][thread] so that lanes
+// never conflict on a bank, and the mixed precision described in DESIGN.md:
+// FP64 for positions and for the cancellation-prone terms of the sphere and
+// plane equations, fp32 for everything else.
+#pragma once
+
+#include <stdint.h>
+
+#include "../../include/rt_abi.h"
+#include "../../include/rt_rng.h"
+#include "rt_device_types.h"
+
+#define RT_DEV __device__ __forceinline__
+
+namespace rtdev {
+
+struct f3 {
+    float x, y, z;
+};
+struct d3 {
+    double x, y, z;
+};
+
+RT_DEV f3 make_f3(float x, float y, float z)
+{
+    f3 r;
+    r.x = x;
+    r.y = y;
+    r.z = z;
+    return r;
+}
+RT_DEV f3 operator+(f3 a, f3 b) { return make_f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_DEV f3 operator-(f3 a, f3 b) { return make_f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_DEV f3 operator*(float s, f3 a) { return make_f3(s * a.x, s * a.y, s * a.z); }
+RT_DEV f3 operator*(f3 a, f3 b) { return make_f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_DEV f3 operator-(f3 a) { return make_f3(-a.x, -a.y, -a.z); }
+RT_DEV float dot(f3 a, f3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+RT_DEV f3 cross(f3 a, f3 b) { return make_f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// Vec3.h:117-120 with :96-99: v * (1/len)
+RT_DEV f3 unit(f3 a) { return (1.0f / sqrtf(dot(a, a))) * a; }
+
+// ------------------------------------------------------------------ memory
+// Scene arrays are addressed either as 32-bit shared-memory addresses (SMEM)
+// or as generic pointers to global memory.
+template <bool SMEM> struct Base;
+template <> struct Base<true> {
+    uint32_t a;
+};
+template <> struct Base<false> {
+    const char* a;
+};
+
+template <bool SMEM> RT_DEV float4 Ld4(Base<SMEM> b, uint32_t off);
+template <> RT_DEV float4 Ld4<true>(Base<true> b, uint32_t off)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(b.a + off));
+    return v;
+}
+template <> RT_DEV float4 Ld4<false>(Base<false> b, uint32_t off) { return __ldg(reinterpret_cast<const float4*>(b.a + off)); }
+
+template <bool SMEM> RT_DEV double2 LdD2(Base<SMEM> b, uint32_t off);
+template <> RT_DEV double2 LdD2<true>(Base<true> b, uint32_t off)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(b.a + off));
+    return v;
+}
+template <> RT_DEV double2 LdD2<false>(Base<false> b, uint32_t off) { return __ldg(reinterpret_cast<const double2*>(b.a + off)); }
+
+template <bool SMEM> RT_DEV int32_t LdI(Base<SMEM> b, uint32_t off);
+template <> RT_DEV int32_t LdI<true>(Base<true> b, uint32_t off)
+{
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(b.a + off));
+    return v;
+}
+template <> RT_DEV int32_t LdI<false>(Base<false> b, uint32_t off) { return __ldg(reinterpret_cast<const int32_t*>(b.a + off)); }
+
+template <bool SMEM> struct SceneView {
+    Base<SMEM> nodes, spheres, sphere_material, moving, quads, media, materials;
+    // never staged: textures and their tables
+    const DevTexture* textures;
+    const DevPerlin* perlins;
+    const DevImage* images;
+    uint32_t root_ref;
+};
+
+// Per-thread traversal stack in shared memory: entry(level) = base + level*stride.
+struct Stack {
+    uint32_t base;   // shared address of this thread's level-0 slot
+    uint32_t stride; // bytes between levels = 4*blockDim.x
+    RT_DEV void Push(int sp, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + sp * stride), "r"(v)); }
+    RT_DEV uint32_t Pop(int sp) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + sp * stride));
+        return v;
+    }
+};
+
+// ---------------------------------------------------------------------- ray
+struct Ray {
+    d3 o;       // FP64 origin
+    d3 d;       // direction (primary: FP64; scattered: the fp32 value widened)
+    float time;
+};
+
+// What traversal needs besides the ray: fp32 copies for the slab test.
+struct RaySlab {
+    f3 inv; // 1/d
+    f3 ood; // o/d
+};
+
+RT_DEV RaySlab MakeSlab(const Ray& r)
+{
+    RaySlab s;
+    const f3 df = make_f3((float)r.d.x, (float)r.d.y, (float)r.d.z);
+    // AABB.h:77-93 divides by d; d == 0 gives +-inf and the NaNs of 0*inf are
+    // dropped by fminf/fmaxf exactly as fmin/fmax do in the reference.
+    s.inv = make_f3(1.0f / df.x, 1.0f / df.y, 1.0f / df.z);
+    s.ood = make_f3((float)r.o.x * s.inv.x, (float)r.o.y * s.inv.y, (float)r.o.z * s.inv.z);
+    return s;
+}
+
+// AABB.h:68-98 as fused multiply-adds: t = lo*inv - o*inv.  Returns entry
+// distance, or +inf when the box is missed within [tmin, tmax].
+RT_DEV float SlabEntry(const float4 lo, const float4 hi, const RaySlab& s, float tmin, float tmax)
+{
+    const float x0 = fmaf(lo.x, s.inv.x, -s.ood.x), x1 = fmaf(hi.x, s.inv.x, -s.ood.x);
+    const float y0 = fmaf(lo.y, s.inv.y, -s.ood.y), y1 = fmaf(hi.y, s.inv.y, -s.ood.y);
+    const float z0 = fmaf(lo.z, s.inv.z, -s.ood.z), z1 = fmaf(hi.z, s.inv.z, -s.ood.z);
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    return tf >= tn ? tn : __int_as_float(0x7f800000);
+}
+
+// ------------------------------------------------------------- primitives
+// Sphere.h:22-70.  Roots of a t^2 + 2 b t + c with b, c and the discriminant
+// in FP64 (the centre may be 1000 units away from a hit point whose position
+// matters to 1e-3); the square root and the roots themselves are fp32 -- the
+// winner is refined by FinalizeSphere.  Root order and the open interval
+// (tmin, tmax) follow the reference.  Returns t or -1.
+RT_DEV float SphereRoots(double ocx, double ocy, double ocz, double radius, const Ray& r, double a, double tmin, float tmax)
+{
+    const double b = fma(ocx, r.d.x, fma(ocy, r.d.y, ocz * r.d.z));
+    const double c = fma(ocx, ocx, fma(ocy, ocy, fma(ocz, ocz, -radius * radius)));
+    const double disc = fma(b, b, -a * c);
+    if (!(disc > 0.0)) return -1.0f;
+    const float s = sqrtf((float)disc);
+    const float bf = (float)b, cf = (float)c, af = (float)a;
+    // cancellation-free pair: q has the larger magnitude
+    const float q = bf > 0.0f ? -(bf + s) : (s - bf);
+    float t0, t1; // t0 <= t1
+    if (bf > 0.0f) {
+        t0 = q / af;
+        t1 = cf / q;
+    } else {
+        t0 = cf / q;
+        t1 = q / af;
+    }
+    // tmin is compared in FP64: a medium's second boundary query starts at
+    // t1 + 1e-4 (ConstantMedium.h:63), which fp32 cannot hold beyond t ~ 1000
+    if (t0 < tmax && (double)t0 > tmin) return t0;
+    if (t1 < tmax && (double)t1 > tmin) return t1;
+    return -1.0f;
+}
+
+template <bool SMEM> RT_DEV float HitSphere(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, double tmin, float tmax)
+{
+    const double2 s0 = LdD2<SMEM>(sv.spheres, index * 32u);
+    const double2 s1 = LdD2<SMEM>(sv.spheres, index * 32u + 16u);
+    return SphereRoots(r.o.x - s0.x, r.o.y - s0.y, r.o.z - s1.x, s1.y, r, a, tmin, tmax);
+}
+
+// MovingSphere.h:44-102: centre lerped by the ray's time, then Sphere.
+template <bool SMEM> RT_DEV d3 MovingCentre(const SceneView<SMEM>& sv, uint32_t index, float time, double& radius)
+{
+    const double2 m0 = LdD2<SMEM>(sv.moving, index * 64u);
+    const double2 m1 = LdD2<SMEM>(sv.moving, index * 64u + 16u);
+    const double2 m2 = LdD2<SMEM>(sv.moving, index * 64u + 32u);
+    const double2 m3 = LdD2<SMEM>(sv.moving, index * 64u + 48u);
+    const float rad = __int_as_float(__double2loint(m1.y));
+    const float time0 = __int_as_float(__double2loint(m3.y));
+    const float invDt = __int_as_float(__double2hiint(m3.y));
+    const double frac = (double)((time - time0) * invDt);
+    radius = (double)rad;
+    d3 c;
+    c.x = fma(frac, m2.x, m0.x);
+    c.y = fma(frac, m2.y, m0.y);
+    c.z = fma(frac, m3.x, m1.x);
+    return c;
+}
+
+template <bool SMEM> RT_DEV float HitMoving(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, double tmin, float tmax)
+{
+    double radius;
+    const d3 c = MovingCentre<SMEM>(sv, index, r.time, radius);
+    return SphereRoots(r.o.x - c.x, r.o.y - c.y, r.o.z - c.z, radius, r, a, tmin, tmax);
+}
+
+// Quad.h:54-99.  Plane terms in FP64, interior test in fp32.  Closed interval
+// [tmin, tmax] and closed [0,1] for alpha/beta as in the reference.  Returns t
+// or -1; alpha/beta are written on a hit.
+template <bool SMEM>
+RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double tmin, float tmax, float& alpha, float& beta)
+{
+    const uint32_t off = index * 96u;
+    const double2 q0 = LdD2<SMEM>(sv.quads, off);        // qx qy
+    const double2 q1 = LdD2<SMEM>(sv.quads, off + 16u);  // qz D
+    const double2 q2 = LdD2<SMEM>(sv.quads, off + 32u);  // nx ny
+    const double2 q3 = LdD2<SMEM>(sv.quads, off + 48u);  // nz | wx wy
+    const double nz = q3.x;
+    const double denom = fma(q2.x, r.d.x, fma(q2.y, r.d.y, nz * r.d.z));
+    if (fabs(denom) < 1e-8) return -1.0f;
+    const double num = q1.y - fma(q2.x, r.o.x, fma(q2.y, r.o.y, nz * r.o.z));
+    const float t = (float)num / (float)denom;
+    if ((double)t < tmin || t > tmax) return -1.0f;
+    const float4 q4 = Ld4<SMEM>(sv.quads, off + 64u); // wz ux uy uz   (after wx wy in q3.y)
+    const float4 q5 = Ld4<SMEM>(sv.quads, off + 80u); // vx vy vz mat
+    const float wx = __int_as_float(__double2loint(q3.y)), wy = __int_as_float(__double2hiint(q3.y));
+    const f3 w = make_f3(wx, wy, q4.x);
+    const f3 u = make_f3(q4.y, q4.z, q4.w);
+    const f3 v = make_f3(q5.x, q5.y, q5.z);
+    const double td = (double)t;
+    const f3 planar = make_f3((float)(fma(td, r.d.x, r.o.x) - q0.x), (float)(fma(td, r.d.y, r.o.y) - q0.y),
+                              (float)(fma(td, r.d.z, r.o.z) - q1.x));
+    const float al = dot(w, cross(planar, v));
+    const float be = dot(w, cross(u, planar));
+    if (!(0.0f <= al && al <= 1.0f) || !(0.0f <= be && be <= 1.0f)) return -1.0f;
+    alpha = al;
+    beta = be;
+    return t;
+}
+
+// One leaf-style run of primitives, closest hit with a shrinking tmax
+// (HittableList.h:39-57).  Returns the hit id or RT_HIT_NONE; t in tmax.
+template <int FEAT, bool SMEM>
+RT_DEV uint32_t HitRun(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, double a, double tmin, float& tmax, uint32_t& primTests)
+{
+    const uint32_t type = RT_REF_TYPE(ref), first = RT_REF_FIRST(ref), count = RT_REF_COUNT(ref);
+    uint32_t hit = RT_HIT_NONE;
+    for (uint32_t i = 0; i < count; ++i) {
+        float t;
+        ++primTests;
+        if ((FEAT & RT_FEAT_QUAD) && type == RT_LEAF_QUAD) {
+            float al, be;
+            t = HitQuad<SMEM>(sv, first + i, r, tmin, tmax, al, be);
+        } else if ((FEAT & RT_FEAT_MOVING) && type == RT_LEAF_MOVING) {
+            t = HitMoving<SMEM>(sv, first + i, r, a, tmin, tmax);
+        } else {
+            t = HitSphere<SMEM>(sv, first + i, r, a, tmin, tmax);
+        }
+        if (t >= 0.0f) {
+            tmax = t;
+            hit = RT_HIT_MAKE(type, first + i);
+        }
+    }
+    return hit;
+}
+
+// ConstantMedium.h:52-94.  Two boundary queries, clip to [tmin,tmax], one
+// keyed uniform per visit.  `visits` > 1 reproduces the reference testing a
+// span-1 BVH leaf twice (SURVEY.md trap T2).  Returns the scatter t or -1.
+template <int FEAT, bool SMEM>
+RT_DEV float HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float tmin, float tmax,
+                       uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
+{
+    const float4 m0 = Ld4<SMEM>(sv.media, index * 32u);
+    const float4 m1 = Ld4<SMEM>(sv.media, index * 32u + 16u);
+    const uint32_t bref = (uint32_t)__float_as_int(m0.x);
+    const float negInvDensity = m0.z;
+    const uint32_t mediumId = (uint32_t)__float_as_int(m0.w);
+    const int visits = __float_as_int(m1.x);
+    const float big = 3.402823466e+38f;
+    float t1 = big;
+    if (HitRun<FEAT, SMEM>(sv, bref, r, a, -1.0e300, t1, primTests) == RT_HIT_NONE) return -1.0f;
+    float t2 = big;
+    if (HitRun<FEAT, SMEM>(sv, bref, r, a, (double)t1 + 0.0001, t2, primTests) == RT_HIT_NONE) return -1.0f;
+    const float rayLength = sqrtf((float)a);
+    float best = -1.0f;
+    for (int v = 0; v < visits; ++v) {
+        float e1 = t1, e2 = t2;
+        if (e1 < tmin) e1 = tmin;
+        if (e2 > tmax) e2 = tmax;
+        if (e1 >= e2) break;
+        if (e1 < 0.0f) e1 = 0.0f;
+        const float inside = (e2 - e1) * rayLength;
+        const rt_u4 k = rt_rng_block(seed, pixel, sample, slot, 1u + 2u * mediumId + (uint32_t)v, 0);
+        const float hitDistance = negInvDensity * logf(rt_bits_to_u01(k.x));
+        if (hitDistance > inside) continue;
+        best = e1 + hitDistance / rayLength;
+        tmax = best;
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------- traversal
+// BvhNode.h:101-158 re-designed: children boxes are fetched as one 64-byte
+// pair and tested together, the nearer child is entered first and the other
+// pushed, leaves are contiguous typed runs.  The closest hit is the same
+// minimum over all primitives the reference computes (its order of visiting
+// them does not matter: media draws are keyed, not sequential).
+struct TraceResult {
+    uint32_t hit; // RT_HIT_* id or RT_HIT_NONE
+    float t;
+};
+
+template <int FEAT, bool SMEM>
+RT_DEV TraceResult Trace(const SceneView<SMEM>& sv, const Ray& r, float tmin, const Stack& stack, uint32_t seed,
+                         uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& nodeTests, uint32_t& primTests)
+{
+    const RaySlab slab = MakeSlab(r);
+    const double a = fma(r.d.x, r.d.x, fma(r.d.y, r.d.y, r.d.z * r.d.z));
+    TraceResult res;
+    res.hit = RT_HIT_NONE;
+    res.t = 3.402823466e+38f;
+    uint32_t ref = sv.root_ref;
+    int sp = 0;
+    while (true) {
+        if (!(ref & RT_REF_LEAF)) {
+            const uint32_t off = ref * 32u;
+            const float4 lo0 = Ld4<SMEM>(sv.nodes, off);
+            const float4 hi0 = Ld4<SMEM>(sv.nodes, off + 16u);
+            const float4 lo1 = Ld4<SMEM>(sv.nodes, off + 32u);
+            const float4 hi1 = Ld4<SMEM>(sv.nodes, off + 48u);
+            nodeTests += 2;
+            const float e0 = SlabEntry(lo0, hi0, slab, tmin, res.t);
+            const float e1 = SlabEntry(lo1, hi1, slab, tmin, res.t);
+            const uint32_t r0 = (uint32_t)__float_as_int(lo0.w), r1 = (uint32_t)__float_as_int(lo1.w);
+            const bool h0 = e0 < 3.0e38f, h1 = e1 < 3.0e38f;
+            if (h0 && h1) {
+                const bool swap = e1 < e0;
+                stack.Push(sp++, swap ? r0 : r1);
+                ref = swap ? r1 : r0;
+                continue;
+            }
+            if (h0 || h1) {
+                ref = h0 ? r0 : r1;
+                continue;
+            }
+        } else {
+            if ((FEAT & RT_FEAT_MEDIUM) && RT_REF_TYPE(ref) == RT_LEAF_MEDIUM) {
+                const uint32_t m = RT_REF_FIRST(ref);
+                const float t = HitMedium<FEAT, SMEM>(sv, m, r, a, tmin, res.t, seed, pixel, sample, slot, primTests);
+                if (t >= 0.0f) {
+                    res.t = t;
+                    res.hit = RT_HIT_MAKE(RT_LEAF_MEDIUM, m);
+                }
+            } else {
+                const uint32_t h = HitRun<FEAT, SMEM>(sv, ref, r, a, (double)tmin, res.t, primTests);
+                if (h != RT_HIT_NONE) res.hit = h;
+            }
+        }
+        if (sp == 0) break;
+        ref = stack.Pop(--sp);
+    }
+    return res;
+}
+
+// ------------------------------------------------------------ hit records
+// Hittable.h:11-31, filled for the winning primitive only.
+struct Hit {
+    d3 p;          // FP64 hit point
+    f3 n;          // shading normal (faces the ray)
+    f3 outward;    // geometric outward normal (sphere UV)
+    float u, v;    // quad: alpha, beta; sphere: filled on demand
+    bool front;
+    int32_t material;
+};
+
+RT_DEV void SetFaceNormal(Hit& h, f3 dir, f3 outward)
+{
+    h.front = dot(dir, outward) < 0.0f;
+    h.n = h.front ? outward : -outward;
+    h.outward = outward;
+}
+
+// Re-solves the winning sphere in FP64: one Newton step on
+// f(t) = a t^2 + 2 b t + c from the fp32 root puts the hit point on the sphere
+// to ~1e-15 relative, so the normal (P-C)/r is as good as fp32 can hold.
+RT_DEV void FinalizeSphereAt(d3 c, double radius, const Ray& r, float t, Hit& h)
+{
+    const double ocx = r.o.x - c.x, ocy = r.o.y - c.y, ocz = r.o.z - c.z;
+    const double a = fma(r.d.x, r.d.x, fma(r.d.y, r.d.y, r.d.z * r.d.z));
+    const double b = fma(ocx, r.d.x, fma(ocy, r.d.y, ocz * r.d.z));
+    const double cc = fma(ocx, ocx, fma(ocy, ocy, fma(ocz, ocz, -radius * radius)));
+    double td = (double)t;
+    const double f = fma(fma(a, td, 2.0 * b), td, cc);
+    const double fp = 2.0 * fma(a, td, b);
+    td -= (double)((float)f / (float)fp);
+    h.p.x = fma(td, r.d.x, r.o.x);
+    h.p.y = fma(td, r.d.y, r.o.y);
+    h.p.z = fma(td, r.d.z, r.o.z);
+    const float invR = 1.0f / (float)radius;
+    const f3 outward = make_f3((float)(h.p.x - c.x) * invR, (float)(h.p.y - c.y) * invR, (float)(h.p.z - c.z) * invR);
+    SetFaceNormal(h, make_f3((float)r.d.x, (float)r.d.y, (float)r.d.z), outward);
+}
+
+template <int FEAT, bool SMEM> RT_DEV void FinalizeHit(const SceneView<SMEM>& sv, const Ray& r, const TraceResult& tr, Hit& h)
+{
+    const uint32_t type = RT_HIT_TYPE(tr.hit), index = RT_HIT_INDEX(tr.hit);
+    h.u = 0.0f;
+    h.v = 0.0f;
+    if ((FEAT & RT_FEAT_MEDIUM) && type == RT_LEAF_MEDIUM) {
+        // ConstantMedium.h:86-91: arbitrary normal, front face, phase material
+        const float4 m0 = Ld4<SMEM>(sv.media, index * 32u);
+        const double td = (double)tr.t;
+        h.p.x = fma(td, r.d.x, r.o.x);
+        h.p.y = fma(td, r.d.y, r.o.y);
+        h.p.z = fma(td, r.d.z, r.o.z);
+        h.n = make_f3(1.0f, 0.0f, 0.0f);
+        h.outward = h.n;
+        h.front = true;
+        h.material = __float_as_int(m0.y);
+    } else if ((FEAT & RT_FEAT_QUAD) && type == RT_LEAF_QUAD) {
+        const uint32_t off = index * 96u;
+        const double2 q0 = LdD2<SMEM>(sv.quads, off);
+        const double2 q1 = LdD2<SMEM>(sv.quads, off + 16u);
+        const double2 q2 = LdD2<SMEM>(sv.quads, off + 32u);
+        const double2 q3 = LdD2<SMEM>(sv.quads, off + 48u);
+        const float4 q4 = Ld4<SMEM>(sv.quads, off + 64u);
+        const float4 q5 = Ld4<SMEM>(sv.quads, off + 80u);
+        const double nz = q3.x;
+        const double denom = fma(q2.x, r.d.x, fma(q2.y, r.d.y, nz * r.d.z));
+        const double num = q1.y - fma(q2.x, r.o.x, fma(q2.y, r.o.y, nz * r.o.z));
+        // division refined once in FP64: t = t0 + (num - t0*denom)/denom
+        double td = (double)((float)num / (float)denom);
+        td += (double)((float)fma(-td, denom, num) / (float)denom);
+        h.p.x = fma(td, r.d.x, r.o.x);
+        h.p.y = fma(td, r.d.y, r.o.y);
+        h.p.z = fma(td, r.d.z, r.o.z);
+        const f3 w = make_f3(__int_as_float(__double2loint(q3.y)), __int_as_float(__double2hiint(q3.y)), q4.x);
+        const f3 u = make_f3(q4.y, q4.z, q4.w);
+        const f3 v = make_f3(q5.x, q5.y, q5.z);
+        const f3 planar = make_f3((float)(h.p.x - q0.x), (float)(h.p.y - q0.y), (float)(h.p.z - q1.x));
+        h.u = dot(w, cross(planar, v));
+        h.v = dot(w, cross(u, planar));
+        h.material = __float_as_int(q5.w);
+        SetFaceNormal(h, make_f3((float)r.d.x, (float)r.d.y, (float)r.d.z), make_f3((float)q2.x, (float)q2.y, (float)nz));
+    } else if ((FEAT & RT_FEAT_MOVING) && type == RT_LEAF_MOVING) {
+        double radius;
+        const d3 c = MovingCentre<SMEM>(sv, index, r.time, radius);
+        FinalizeSphereAt(c, radius, r, tr.t, h);
+        h.material = __double2hiint(LdD2<SMEM>(sv.moving, index * 64u + 16u).y);
+    } else {
+        const double2 s0 = LdD2<SMEM>(sv.spheres, index * 32u);
+        const double2 s1 = LdD2<SMEM>(sv.spheres, index * 32u + 16u);
+        d3 c;
+        c.x = s0.x;
+        c.y = s0.y;
+        c.z = s1.x;
+        FinalizeSphereAt(c, s1.y, r, tr.t, h);
+        h.material = LdI<SMEM>(sv.sphere_material, index * 4u);
+    }
+}
+
+// ----------------------------------------------------------------- textures
+// Perlin.h:38-139.  Lattice cell and fractions from the FP64 point (octave 6
+// scales it by 64, where fp32 would have lost the fraction); the rest fp32.
+RT_DEV float PerlinNoise(const DevPerlin* __restrict__ t, double px, double py, double pz)
+{
+    const double fx = floor(px), fy = floor(py), fz = floor(pz);
+    const float u = (float)(px - fx), v = (float)(py - fy), w = (float)(pz - fz);
+    const int i = (int)fx, j = (int)fy, k = (int)fz;
+    const float uu = u * u * (3.0f - 2.0f * u);
+    const float vv = v * v * (3.0f - 2.0f * v);
+    const float ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                const int hsh = __ldg(&t->perm_x[(i + di) & 255]) ^ __ldg(&t->perm_y[(j + dj) & 255]) ^
+                                __ldg(&t->perm_z[(k + dk) & 255]);
+                const float4 c = __ldg(reinterpret_cast<const float4*>(&t->ranvec[hsh][0]));
+                const float wu = di ? uu : 1.0f - uu, wv = dj ? vv : 1.0f - vv, wwt = dk ? ww : 1.0f - ww;
+                accum += wu * wv * wwt * (c.x * (u - di) + c.y * (v - dj) + c.z * (w - dk));
+            }
+    return accum;
+}
+
+RT_DEV float PerlinTurb(const DevPerlin* __restrict__ t, d3 p, int depth)
+{
+    float accum = 0.0f, weight = 1.0f;
+    for (int i = 0; i < depth; ++i) {
+        accum += weight * PerlinNoise(t, p.x, p.y, p.z);
+        weight *= 0.5f;
+        p.x *= 2.0;
+        p.y *= 2.0;
+        p.z *= 2.0;
+    }
+    return fabsf(accum);
+}
+
+// Sphere.h:73-81
+RT_DEV void SphereUV(f3 p, float& u, float& v)
+{
+    const float pi = 3.14159265358979323846f;
+    const float theta = acosf(-p.y);
+    const float phi = atan2f(-p.z, p.x) + pi;
+    u = phi / (2.0f * pi);
+    v = theta / pi;
+}
+
+// Texture.h:29-176
+template <bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv, int tex, const Hit& h, bool sphereLike)
+{
+    for (int guard = 0; guard < 16; ++guard) {
+        const DevTexture* t = &sv.textures[tex];
+        const int type = __ldg(&t->type);
+        if (type == RT_TEX_SOLID) return make_f3(__ldg(&t->r), __ldg(&t->g), __ldg(&t->b));
+        if (type == RT_TEX_CHECKER) {
+            // Texture.h:70-81: the parity decision is taken on the FP64 point
+            const double inv = __ldg(&t->inv_scale);
+            const int xi = (int)floor(inv * h.p.x), yi = (int)floor(inv * h.p.y), zi = (int)floor(inv * h.p.z);
+            tex = ((xi + yi + zi) % 2 == 0) ? __ldg(&t->even) : __ldg(&t->odd);
+            continue;
+        }
+        if (type == RT_TEX_IMAGE) {
+            // Texture.h:110-133: nearest texel, v flipped, cyan when there is no image
+            const int idx = __ldg(&t->index);
+            if (idx < 0) return make_f3(0.0f, 1.0f, 1.0f);
+            const DevImage im = sv.images[idx];
+            if (im.height <= 0 || im.rgb == nullptr) return make_f3(0.0f, 1.0f, 1.0f);
+            float u = h.u, v = h.v;
+            if (sphereLike) SphereUV(h.outward, u, v);
+            u = fminf(fmaxf(u, 0.0f), 1.0f);
+            v = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+            int i = (int)(u * (float)im.width), j = (int)(v * (float)im.height);
+            if (i >= im.width) i = im.width - 1;
+            if (j >= im.height) j = im.height - 1;
+            const uint8_t* px = im.rgb + ((size_t)j * im.width + i) * 3;
+            const float cs = 1.0f / 255.0f;
+            return make_f3(cs * __ldg(px), cs * __ldg(px + 1), cs * __ldg(px + 2));
+        }
+        // Texture.h:159-165: marble
+        const DevPerlin* pt = &sv.perlins[__ldg(&t->index)];
+        const float phase = (float)((double)__ldg(&t->scale) * h.p.z) + 10.0f * PerlinTurb(pt, h.p, 7);
+        const float g = 0.5f * (1.0f + sinf(phase));
+        return make_f3(g, g, g);
+    }
+    return make_f3(0.0f, 0.0f, 0.0f);
+}
+
+// ---------------------------------------------------------------- scatter
+struct DrawStream {
+    uint32_t seed, pixel, sample, slot, dim;
+    rt_u4 cur;
+    RT_DEV void Begin(uint32_t seed_, uint32_t pixel_, uint32_t sample_, uint32_t slot_)
+    {
+        seed = seed_;
+        pixel = pixel_;
+        sample = sample_;
+        slot = slot_;
+        dim = 0;
+    }
+    RT_DEV float Next()
+    {
+        const uint32_t lane = dim & 3u;
+        if (lane == 0) cur = rt_rng_block(seed, pixel, sample, slot, 0, dim >> 2);
+        ++dim;
+        return rt_bits_to_u01(rt_u4_lane(cur, lane));
+    }
+};
+
+// Material.h:14-24
+RT_DEV f3 RandomInUnitSphere(DrawStream& rng)
+{
+    f3 p;
+    do {
+        const float x = rng.Next();
+        const float y = rng.Next();
+        const float z = rng.Next();
+        p = make_f3(2.0f * x - 1.0f, 2.0f * y - 1.0f, 2.0f * z - 1.0f);
+    } while (dot(p, p) >= 1.0f);
+    return p;
+}
+
+RT_DEV f3 Reflect(f3 v, f3 n) { return v - (2.0f * dot(v, n)) * n; } // Vec3.h:122-125
+
+// Returns false when the path ends (light, or absorbed by metal).  On true,
+// `dir` is the scattered direction (not normalised, like the reference) and
+// `atten` the attenuation.  `emitted` is Material::Emitted (black unless light).
+template <int FEAT, bool SMEM>
+RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, f3 dirIn, bool sphereLike, DrawStream& rng, f3& atten, f3& dir,
+                    f3& emitted)
+{
+    const float4 m0 = Ld4<SMEM>(sv.materials, (uint32_t)h.material * 32u);
+    const float4 m1 = Ld4<SMEM>(sv.materials, (uint32_t)h.material * 32u + 16u);
+    const int type = __float_as_int(m1.x);
+    const int tex = __float_as_int(m1.y);
+    emitted = make_f3(0.0f, 0.0f, 0.0f);
+    f3 colour = make_f3(m0.x, m0.y, m0.z);
+    if ((FEAT & RT_FEAT_TEXTURE) && tex >= 0 && type != RT_MAT_METAL && type != RT_MAT_DIELECTRIC)
+        colour = TextureValue<SMEM>(sv, tex, h, sphereLike);
+    if (type == RT_MAT_LAMBERTIAN) { // Material.h:68-86
+        dir = h.n + RandomInUnitSphere(rng);
+        if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = h.n;
+        atten = colour;
+        return true;
+    }
+    if (type == RT_MAT_METAL) { // Metal.h:18-30 (draws even when fuzz == 0)
+        const f3 reflected = Reflect(unit(dirIn), h.n);
+        dir = reflected + m0.w * RandomInUnitSphere(rng);
+        atten = colour;
+        return dot(dir, h.n) > 0.0f;
+    }
+    if (type == RT_MAT_DIELECTRIC) { // Dielectric.h:18-68, Vec3.h:127-141
+        atten = make_f3(1.0f, 1.0f, 1.0f);
+        const float ratio = h.front ? 1.0f / m0.w : m0.w;
+        const f3 ud = unit(dirIn);
+        const float cosTheta = fminf(dot(-ud, h.n), 1.0f);
+        const float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+        bool reflect = ratio * sinTheta > 1.0f;
+        if (!reflect) { // no draw on total internal reflection
+            float r0 = (1.0f - ratio) / (1.0f + ratio);
+            r0 = r0 * r0;
+            const float k = 1.0f - cosTheta;
+            const float k2 = k * k;
+            reflect = r0 + (1.0f - r0) * (k2 * k2 * k) > rng.Next();
+        }
+        if (reflect) {
+            dir = Reflect(ud, h.n);
+        } else {
+            const f3 perp = ratio * (ud + cosTheta * h.n);
+            const f3 para = -sqrtf(fabsf(1.0f - dot(perp, perp))) * h.n;
+            dir = perp + para;
+        }
+        return true;
+    }
+    if (type == RT_MAT_ISOTROPIC) { // Material.h:151-162
+        dir = unit(RandomInUnitSphere(rng));
+        atten = colour;
+        return true;
+    }
+    emitted = colour; // DiffuseLight, Material.h:116-128
+    return false;
+}
+
+// ------------------------------------------------------------------- camera
+// kernel.cu:140-142 + Camera.h:10-19,76-85: jitter (int + float sum in fp32),
+// lens disk by rejection (always drawn), shutter time (always drawn).
+RT_DEV Ray CameraRay(const DevCamera& cam, int i, int j, DrawStream& rng)
+{
+    const float fu = (float)i + rng.Next();
+    const float fv = (float)j + rng.Next();
+    const double s = (double)fu / (double)cam.width;
+    const double t = (double)fv / (double)cam.height;
+    float px, py;
+    do {
+        const float x = rng.Next();
+        const float y = rng.Next();
+        px = 2.0f * x - 1.0f;
+        py = 2.0f * y - 1.0f;
+    } while (px * px + py * py >= 1.0f);
+    const double rdx = cam.lens_radius * (double)px, rdy = cam.lens_radius * (double)py;
+    const double offx = cam.u[0] * rdx + cam.v[0] * rdy;
+    const double offy = cam.u[1] * rdx + cam.v[1] * rdy;
+    const double offz = cam.u[2] * rdx + cam.v[2] * rdy;
+    Ray r;
+    r.time = cam.time0 + rng.Next() * (cam.time1 - cam.time0);
+    r.o.x = cam.origin[0] + offx;
+    r.o.y = cam.origin[1] + offy;
+    r.o.z = cam.origin[2] + offz;
+    // primary directions stay FP64 (scattered ones are fp32 values widened)
+    r.d.x = cam.llc[0] + s * cam.horiz[0] + t * cam.vert[0] - cam.origin[0] - offx;
+    r.d.y = cam.llc[1] + s * cam.horiz[1] + t * cam.vert[1] - cam.origin[1] - offy;
+    r.d.z = cam.llc[2] + s * cam.horiz[2] + t * cam.vert[2] - cam.origin[2] - offz;
+    return r;
+}
+
+} // namespace rtdev

@@ -1,0 +1,85 @@
+"""Shared fixtures.
+
+`-m "not gpu"` tests run on a CPU-only box: they exercise the oracle, the host
+scene surface and the library's exports.  `-m gpu` tests are the parity tests
+proper and render through the C ABI on a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from raytracinginoneweekendincuda_b200 import _abi as A  # noqa: E402
+from raytracinginoneweekendincuda_b200 import _build  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Make sure the in-tree libraries exist (compiles them when a toolchain is here)."""
+    if not (os.path.exists(_build.lib_path()) and os.path.exists(_build.oracle_path())):
+        _build.build_product()
+        _build.build_oracle()
+    return True
+
+
+@pytest.fixture(scope="session")
+def lib(built):
+    from raytracinginoneweekendincuda_b200 import load_library
+    return load_library()
+
+
+@pytest.fixture(scope="session")
+def oracle(built):
+    o = C.CDLL(_build.oracle_path())
+    A.declare_oracle(o)
+    return o
+
+
+@pytest.fixture(scope="session")
+def ref_stream():
+    """The reference's own classes compiled for the host (only where oracle/_ref was built)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_stream.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_stream.so not built (needs /root/reference)")
+    r = C.CDLL(path)
+    A.declare_ref_stream(r)
+    return r
+
+
+@pytest.fixture(scope="session")
+def earth():
+    from raytracinginoneweekendincuda_b200 import load_earth_fixture
+    e = load_earth_fixture()
+    assert e is not None, "tests/golden/earthmap_rgb8.npz missing"
+    return e
+
+
+def oracle_render(oracle, scene, cam, s0, s1, seed=1984, bvh=1, precision=64, threads=0):
+    out = np.zeros((cam.image_height, cam.image_width, 3), np.float64)
+    st = A.oracle_stats()
+    rc = oracle.oracle_render(scene.desc, C.byref(cam), s0, s1, seed, bvh, precision, threads or (os.cpu_count() or 1),
+                              out.ctypes.data, C.byref(st))
+    assert rc == 0
+    return out, st
+
+
+def has_gpu() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
