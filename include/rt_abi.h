@@ -256,6 +256,13 @@ const char* rt_last_error(void);
 float rt_rng_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t domain,
                      uint32_t dim);
 
+/* Measures the device's fp32 FMA throughput with dependent-free FFMA chains
+ * (the roofline denominator of this path: it is FP32-issue bound, not HBM). */
+int rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_count);
+
+/* sizeof() of an ABI struct by name, for binding self-checks; -1 if unknown. */
+int rt_abi_sizeof(const char* name);
+
 /* Writes the reference's P3 text PPM (kernel.cu:696-723) from srgb8 (top row first). */
 int rt_write_ppm(const char* path, const uint8_t* srgb8, int32_t width, int32_t height);
 

@@ -247,6 +247,28 @@ __global__ void ResolveKernel(const float* __restrict__ accum, float* __restrict
     }
 }
 
+// Roofline denominator: dependent-free FFMA chains, 2 flop per FFMA per lane.
+__global__ void FmaPeakKernel(float* out, int iters)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a0 = fmaf(a0, m, c);
+            a1 = fmaf(a1, m, c);
+            a2 = fmaf(a2, m, c);
+            a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c);
+            a5 = fmaf(a5, m, c);
+            a6 = fmaf(a6, m, c);
+            a7 = fmaf(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 using KernelFn = void (*)(const DevScene, const DevCamera, const RenderArgs);
 
 template <int FEAT> KernelFn PickKernel(bool smem, bool stats)
@@ -305,6 +327,7 @@ struct rt_scene_s {
     size_t accumFloats = 0;
     float* linearStage = nullptr;
     uint8_t* srgbStage = nullptr;
+    size_t linearStageFloats = 0, srgbStageBytes = 0;
     unsigned long long* stats = nullptr;
     unsigned int* tileCounter = nullptr;
     cudaStream_t lastStream = nullptr;
@@ -554,8 +577,20 @@ int rt_readback(rt_scene_handle h, const float* accum, float* linear_rgb, uint8_
     }
     cudaStream_t stream = h->lastStream;
     if (linear_rgb || srgb8) {
-        if (linear_rgb && !h->linearStage) RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->linearStage), nFloats * sizeof(float)));
-        if (srgb8 && !h->srgbStage) RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->srgbStage), nFloats));
+        if (linear_rgb && h->linearStageFloats < nFloats) {
+            if (h->linearStage) RT_CUDA(cudaFree(h->linearStage));
+            h->linearStage = nullptr;
+            h->linearStageFloats = 0;
+            RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->linearStage), nFloats * sizeof(float)));
+            h->linearStageFloats = nFloats;
+        }
+        if (srgb8 && h->srgbStageBytes < nFloats) {
+            if (h->srgbStage) RT_CUDA(cudaFree(h->srgbStage));
+            h->srgbStage = nullptr;
+            h->srgbStageBytes = 0;
+            RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->srgbStage), nFloats));
+            h->srgbStageBytes = nFloats;
+        }
         const int n = W * H;
         const float invSpp = 1.0f / (float)h->lastCam.samples_per_pixel;
         ResolveKernel<<<(n + 255) / 256, 256, 0, stream>>>(src, linear_rgb ? h->linearStage : nullptr,
@@ -644,6 +679,45 @@ int rt_write_ppm(const char* path, const uint8_t* srgb8, int32_t width, int32_t 
     }
     std::fwrite(buf.data(), 1, buf.size(), f);
     std::fclose(f);
+    return RT_OK;
+}
+
+int rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_count)
+{
+    if (!tflops) {
+        rt_set_error("rt_measure_fp32_peak: NULL argument");
+        return RT_ERR_INVALID;
+    }
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || device < 0 || device >= nDev) {
+        rt_set_error("rt_measure_fp32_peak: no such CUDA device");
+        return RT_ERR_NO_DEVICE;
+    }
+    RT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float* out = nullptr;
+    RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&out), (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    RT_CUDA(cudaEventCreate(&e0));
+    RT_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        RT_CUDA(cudaEventRecord(e0));
+        FmaPeakKernel<<<blocks, threads>>>(out, iters);
+        RT_CUDA(cudaEventRecord(e1));
+        RT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        RT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
     return RT_OK;
 }
 

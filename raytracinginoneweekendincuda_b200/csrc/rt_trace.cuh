@@ -144,17 +144,21 @@ RT_DEV float SlabEntry(const float4 lo, const float4 hi, const RaySlab& s, float
 }
 
 // ------------------------------------------------------------- primitives
+// Primitive tests return the hit distance, or RT_MISS.  Distances may be
+// negative (a medium's boundary is queried over (-inf, +inf),
+// ConstantMedium.h:60), so the sentinel is a value no test can produce.
+#define RT_MISS (-3.0e38f)
 // Sphere.h:22-70.  Roots of a t^2 + 2 b t + c with b, c and the discriminant
 // in FP64 (the centre may be 1000 units away from a hit point whose position
 // matters to 1e-3); the square root and the roots themselves are fp32 -- the
 // winner is refined by FinalizeSphere.  Root order and the open interval
-// (tmin, tmax) follow the reference.  Returns t or -1.
+// (tmin, tmax) follow the reference.  Returns t or RT_MISS.
 RT_DEV float SphereRoots(double ocx, double ocy, double ocz, double radius, const Ray& r, double a, double tmin, float tmax)
 {
     const double b = fma(ocx, r.d.x, fma(ocy, r.d.y, ocz * r.d.z));
     const double c = fma(ocx, ocx, fma(ocy, ocy, fma(ocz, ocz, -radius * radius)));
     const double disc = fma(b, b, -a * c);
-    if (!(disc > 0.0)) return -1.0f;
+    if (!(disc > 0.0)) return RT_MISS;
     const float s = sqrtf((float)disc);
     const float bf = (float)b, cf = (float)c, af = (float)a;
     // cancellation-free pair: q has the larger magnitude
@@ -171,7 +175,7 @@ RT_DEV float SphereRoots(double ocx, double ocy, double ocz, double radius, cons
     // t1 + 1e-4 (ConstantMedium.h:63), which fp32 cannot hold beyond t ~ 1000
     if (t0 < tmax && (double)t0 > tmin) return t0;
     if (t1 < tmax && (double)t1 > tmin) return t1;
-    return -1.0f;
+    return RT_MISS;
 }
 
 template <bool SMEM> RT_DEV float HitSphere(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, double tmin, float tmax)
@@ -209,7 +213,7 @@ template <bool SMEM> RT_DEV float HitMoving(const SceneView<SMEM>& sv, uint32_t 
 
 // Quad.h:54-99.  Plane terms in FP64, interior test in fp32.  Closed interval
 // [tmin, tmax] and closed [0,1] for alpha/beta as in the reference.  Returns t
-// or -1; alpha/beta are written on a hit.
+// or RT_MISS; alpha/beta are written on a hit.
 template <bool SMEM>
 RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double tmin, float tmax, float& alpha, float& beta)
 {
@@ -220,10 +224,10 @@ RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, do
     const double2 q3 = LdD2<SMEM>(sv.quads, off + 48u);  // nz | wx wy
     const double nz = q3.x;
     const double denom = fma(q2.x, r.d.x, fma(q2.y, r.d.y, nz * r.d.z));
-    if (fabs(denom) < 1e-8) return -1.0f;
+    if (fabs(denom) < 1e-8) return RT_MISS;
     const double num = q1.y - fma(q2.x, r.o.x, fma(q2.y, r.o.y, nz * r.o.z));
     const float t = (float)num / (float)denom;
-    if ((double)t < tmin || t > tmax) return -1.0f;
+    if ((double)t < tmin || t > tmax) return RT_MISS;
     const float4 q4 = Ld4<SMEM>(sv.quads, off + 64u); // wz ux uy uz   (after wx wy in q3.y)
     const float4 q5 = Ld4<SMEM>(sv.quads, off + 80u); // vx vy vz mat
     const float wx = __int_as_float(__double2loint(q3.y)), wy = __int_as_float(__double2hiint(q3.y));
@@ -235,7 +239,7 @@ RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, do
                               (float)(fma(td, r.d.z, r.o.z) - q1.x));
     const float al = dot(w, cross(planar, v));
     const float be = dot(w, cross(u, planar));
-    if (!(0.0f <= al && al <= 1.0f) || !(0.0f <= be && be <= 1.0f)) return -1.0f;
+    if (!(0.0f <= al && al <= 1.0f) || !(0.0f <= be && be <= 1.0f)) return RT_MISS;
     alpha = al;
     beta = be;
     return t;
@@ -259,7 +263,7 @@ RT_DEV uint32_t HitRun(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, do
         } else {
             t = HitSphere<SMEM>(sv, first + i, r, a, tmin, tmax);
         }
-        if (t >= 0.0f) {
+        if (t != RT_MISS) {
             tmax = t;
             hit = RT_HIT_MAKE(type, first + i);
         }
@@ -269,7 +273,8 @@ RT_DEV uint32_t HitRun(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, do
 
 // ConstantMedium.h:52-94.  Two boundary queries, clip to [tmin,tmax], one
 // keyed uniform per visit.  `visits` > 1 reproduces the reference testing a
-// span-1 BVH leaf twice (SURVEY.md trap T2).  Returns the scatter t or -1.
+// span-1 BVH leaf twice (SURVEY.md trap T2).  Returns the scatter t (always
+// >= tmin > 0) or RT_MISS.
 template <int FEAT, bool SMEM>
 RT_DEV float HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float tmin, float tmax,
                        uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
@@ -282,11 +287,11 @@ RT_DEV float HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, 
     const int visits = __float_as_int(m1.x);
     const float big = 3.402823466e+38f;
     float t1 = big;
-    if (HitRun<FEAT, SMEM>(sv, bref, r, a, -1.0e300, t1, primTests) == RT_HIT_NONE) return -1.0f;
+    if (HitRun<FEAT, SMEM>(sv, bref, r, a, -1.0e300, t1, primTests) == RT_HIT_NONE) return RT_MISS;
     float t2 = big;
-    if (HitRun<FEAT, SMEM>(sv, bref, r, a, (double)t1 + 0.0001, t2, primTests) == RT_HIT_NONE) return -1.0f;
+    if (HitRun<FEAT, SMEM>(sv, bref, r, a, (double)t1 + 0.0001, t2, primTests) == RT_HIT_NONE) return RT_MISS;
     const float rayLength = sqrtf((float)a);
-    float best = -1.0f;
+    float best = RT_MISS;
     for (int v = 0; v < visits; ++v) {
         float e1 = t1, e2 = t2;
         if (e1 < tmin) e1 = tmin;
@@ -351,7 +356,7 @@ RT_DEV TraceResult Trace(const SceneView<SMEM>& sv, const Ray& r, float tmin, co
             if ((FEAT & RT_FEAT_MEDIUM) && RT_REF_TYPE(ref) == RT_LEAF_MEDIUM) {
                 const uint32_t m = RT_REF_FIRST(ref);
                 const float t = HitMedium<FEAT, SMEM>(sv, m, r, a, tmin, res.t, seed, pixel, sample, slot, primTests);
-                if (t >= 0.0f) {
+                if (t != RT_MISS) {
                     res.t = t;
                     res.hit = RT_HIT_MAKE(RT_LEAF_MEDIUM, m);
                 }
