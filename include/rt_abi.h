@@ -256,6 +256,12 @@ const char* rt_last_error(void);
 float rt_rng_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t domain,
                      uint32_t dim);
 
+/* Test hook: renders `sample` of the whole frame with the instrumented kernel and
+ * returns, for the path of (pixel, sample), one 8-float record per bounce:
+ * {hit id bits, t, material bits, front face, p.x, p.y, p.z, 1}; unused records are 0. */
+int rt_debug_trace_path(rt_scene_handle scene, const rt_camera* cam, const rt_render_params* p, int32_t pixel,
+                        int32_t sample, float* records, int32_t max_records);
+
 /* Measures the device's fp32 FMA throughput with dependent-free FFMA chains
  * (the roofline denominator of this path: it is FP32-issue bound, not HBM). */
 int rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_count);

@@ -947,6 +947,48 @@ int oracle_bvh_topology(const rt_scene_desc* scene, int32_t* out, int32_t capaci
     return n;
 }
 
+// Debug aid: the path of (pixel i,j; sample) bounce by bounce, 8 doubles per
+// record {hit(1/0), t, material, front, p.x, p.y, p.z, material type}; returns
+// the number of records written.  Follows RayColor (kernel.cu:65-98) like above.
+int oracle_trace_path(const rt_scene_desc* scene, const rt_camera* cam, int i, int j, int sample, uint32_t seed,
+                      double* records, int max_records)
+{
+    Scene<double> s;
+    if (!LoadScene(scene, s) || !cam || !records) return -1;
+    const Cam<double> c(*cam);
+    Stats st;
+    Stream rng;
+    rng.seed = seed;
+    rng.stats = &st;
+    rng.pixel = (uint32_t)(j * c.W + i);
+    rng.sample = (uint32_t)sample;
+    rng.Begin(0);
+    const float fu = (float)i + rng.Next();
+    const float fv = (float)j + rng.Next();
+    Ray<double> ray = c.GetRay((double)fu / double(c.W), (double)fv / double(c.H), rng);
+    int n = 0;
+    for (int bounce = 0; bounce < c.maxDepth && n < max_records; ++bounce) {
+        rng.Begin((uint32_t)bounce + 1u);
+        HitRec<double> rec;
+        const bool hit = HitWorldBvh(s, ray, 0.001, Limits<double>::Max(), rec, rng, st);
+        double* o = records + 8 * n++;
+        o[0] = hit ? 1.0 : 0.0;
+        if (!hit) break;
+        o[1] = rec.t;
+        o[2] = rec.material;
+        o[3] = rec.front ? 1.0 : 0.0;
+        o[4] = rec.p[0];
+        o[5] = rec.p[1];
+        o[6] = rec.p[2];
+        o[7] = s.materials[rec.material].type;
+        Ray<double> scattered;
+        V3<double> atten;
+        if (!Scatter(s, ray, rec, atten, scattered, rng)) break;
+        ray = scattered;
+    }
+    return n;
+}
+
 // Texture lookup exactly as the integrator does it (unit tests).
 int oracle_texture_value(const rt_scene_desc* scene, int texture, double u, double v, const double* p, double* rgb)
 {

@@ -156,6 +156,9 @@ def declare_device(lib: C.CDLL) -> None:
     lib.rt_rng_uniform.argtypes = [C.c_uint32] * 6
     lib.rt_write_ppm.restype = C.c_int
     lib.rt_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.rt_debug_trace_path.restype = C.c_int
+    lib.rt_debug_trace_path.argtypes = [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_params), C.c_int32,
+                                        C.c_int32, C.c_void_p, C.c_int32]
     lib.rt_measure_fp32_peak.restype = C.c_int
     lib.rt_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.rt_abi_sizeof.restype = C.c_int
@@ -166,6 +169,9 @@ def declare_oracle(lib: C.CDLL) -> None:
     lib.oracle_render.restype = C.c_int
     lib.oracle_render.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_camera), C.c_int, C.c_int, C.c_uint32,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(oracle_stats)]
+    lib.oracle_trace_path.restype = C.c_int
+    lib.oracle_trace_path.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_camera), C.c_int, C.c_int, C.c_int,
+                                      C.c_uint32, C.c_void_p, C.c_int]
     lib.oracle_rng_uniform.restype = C.c_float
     lib.oracle_rng_uniform.argtypes = [C.c_uint32] * 6
     lib.oracle_bvh_topology.restype = C.c_int

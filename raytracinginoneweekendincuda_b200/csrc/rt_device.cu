@@ -58,6 +58,9 @@ struct RenderArgs {
     int sampleBegin, sampleEnd;
     uint32_t seed;
     int tilesX, tilesY;
+    // test hook (STATS instantiations only): per-bounce records of one (pixel, sample) path
+    int debugPixel, debugSample;
+    float* debugOut; // [max_depth][8]: hit id, t, material, front, p.x, p.y, p.z, 1
     // byte sizes of the staged arrays (SMEM variant)
     uint32_t nodesBytes, spheresBytes, sphereMatBytes, movingBytes, quadsBytes, mediaBytes, materialsBytes;
 };
@@ -169,6 +172,17 @@ __global__ void RenderMega(const DevScene scene, const DevCamera cam, const Rend
                     Hit h;
                     FinalizeHit<FEAT, SMEM>(sv, ray, tr, h);
                     const uint32_t type = RT_HIT_TYPE(tr.hit);
+                    if (STATS && args.debugOut && (int)pixel == args.debugPixel && sample == args.debugSample) {
+                        float* o = args.debugOut + bounce * 8;
+                        o[0] = __uint_as_float(tr.hit);
+                        o[1] = tr.t;
+                        o[2] = __int_as_float(h.material);
+                        o[3] = h.front ? 1.0f : 0.0f;
+                        o[4] = (float)h.p.x;
+                        o[5] = (float)h.p.y;
+                        o[6] = (float)h.p.z;
+                        o[7] = 1.0f;
+                    }
                     const bool sphereLike = type == RT_LEAF_SPHERE || type == RT_LEAF_MOVING;
                     DrawStream rng;
                     rng.Begin(args.seed, pixel, (uint32_t)sample, (uint32_t)bounce + 1u);
@@ -330,6 +344,8 @@ struct rt_scene_s {
     size_t linearStageFloats = 0, srgbStageBytes = 0;
     unsigned long long* stats = nullptr;
     unsigned int* tileCounter = nullptr;
+    float* debugOut = nullptr; // test hook, 256*8 floats
+    int debugPixel = -1, debugSample = -1;
     cudaStream_t lastStream = nullptr;
     rt_camera lastCam{};
     bool rendered = false;
@@ -496,6 +512,9 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     a.sampleBegin = p->sample_begin;
     a.sampleEnd = p->sample_end;
     a.seed = p->seed;
+    a.debugPixel = h->debugPixel;
+    a.debugSample = h->debugSample;
+    a.debugOut = h->debugPixel >= 0 ? h->debugOut : nullptr;
     a.tilesX = (cam->image_width + kTileW - 1) / kTileW;
     a.tilesY = (cam->image_height + kTileH - 1) / kTileH;
     auto pad16 = [](size_t b) { return (uint32_t)((b + 15) / 16 * 16); };
@@ -512,7 +531,7 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     threads = std::max(32, std::min(1024, (threads / 32) * 32));
     int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;
     const size_t stackBytes = (size_t)threads * 4 * kStackLevels;
-    const bool wantStats = (p->flags & 0x100) != 0;
+    const bool wantStats = (p->flags & 0x100) != 0 || a.debugOut != nullptr;
     const bool smem = !(p->flags & 0x200) && stackBytes + h->stagedBytes <= (size_t)h->maxSmemOptin / (size_t)blocksPerSm;
     const size_t smemBytes = stackBytes + (smem ? h->stagedBytes : 0);
     if (smemBytes > (size_t)h->maxSmemOptin) {
@@ -571,8 +590,8 @@ int rt_readback(rt_scene_handle h, const float* accum, float* linear_rgb, uint8_
     const int W = h->lastCam.image_width, H = h->lastCam.image_height;
     const size_t nFloats = (size_t)W * H * 3;
     const float* src = accum ? accum : h->accum;
-    if (!src) {
-        rt_set_error("rt_readback: no accumulator");
+    if (!src && (linear_rgb || srgb8)) {
+        rt_set_error("rt_readback: no accumulator (the render used a caller-owned one: pass it as `accum`)");
         return RT_ERR_STATE;
     }
     cudaStream_t stream = h->lastStream;
@@ -623,6 +642,7 @@ int rt_scene_free(rt_scene_handle h)
     if (h->srgbStage) cudaFree(h->srgbStage);
     if (h->stats) cudaFree(h->stats);
     if (h->tileCounter) cudaFree(h->tileCounter);
+    if (h->debugOut) cudaFree(h->debugOut);
     delete h->host;
     delete h;
     return RT_OK;
@@ -643,6 +663,29 @@ int rt_scene_get_info(rt_scene_handle h, rt_scene_info* info)
     info->scene_in_smem = h->fitsSmem ? 1 : 0;
     info->device_bytes = h->deviceBytes;
     for (int k = 0; k < 8; ++k) info->medium_visits[k] = h->host->medium_visits[k];
+    return RT_OK;
+}
+
+int rt_debug_trace_path(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p, int32_t pixel,
+                        int32_t sample, float* records, int32_t max_records)
+{
+    if (!h || !cam || !p || !records || max_records <= 0 || max_records > 256) {
+        rt_set_error("rt_debug_trace_path: bad argument");
+        return RT_ERR_INVALID;
+    }
+    RT_CUDA(cudaSetDevice(h->device));
+    if (!h->debugOut) RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->debugOut), 256 * 8 * sizeof(float)));
+    RT_CUDA(cudaMemset(h->debugOut, 0, 256 * 8 * sizeof(float)));
+    h->debugPixel = pixel;
+    h->debugSample = sample;
+    rt_render_params q = *p;
+    q.sample_begin = sample;
+    q.sample_end = sample + 1;
+    const int rc = rt_render(h, cam, &q);
+    h->debugPixel = h->debugSample = -1;
+    if (rc != RT_OK) return rc;
+    RT_CUDA(cudaStreamSynchronize(h->lastStream));
+    RT_CUDA(cudaMemcpy(records, h->debugOut, (size_t)max_records * 8 * sizeof(float), cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 

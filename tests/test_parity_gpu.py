@@ -160,8 +160,10 @@ def test_host_scene_equals_the_scene_the_reference_builds_on_the_gpu(earth, sid)
     host = host[np.lexsort(host.T[::-1])]
     # nvcc contracts a + b*c into an FMA in device code (e.g. `a + 0.9 * RND`,
     # kernel.cu:216; the rotated corners of Instance.h:96-97), g++ -ffp-contract=off
-    # does not: the two scenes may differ in the last bit, never by more.
-    err = np.abs(dev - host) / np.maximum(np.abs(host), 1e-300)
+    # does not: a centre may differ in its last bit, never by more.  A box edge is
+    # centre -+ radius, so the bit is measured against the object's largest coordinate.
+    scale = np.maximum(np.abs(host).max(axis=1, keepdims=True), 1.0)
+    err = np.abs(dev - host) / scale
     assert err.max() <= 4e-16, f"max relative difference {err.max():.3e} (a wrong draw order would give O(1))"
     assert (dev == host).mean() > 0.5
 

@@ -134,3 +134,46 @@ if "dump9" in what:
     r.close()
     np.savez_compressed(os.path.join(OUT, "dump_scene9.npz"), gpu=got, oracle=want / spp)
     print("dumped scene 9")
+
+if "diverge" in what:
+    # per-sample comparison: find (pixel, sample) paths whose radiance differs, dump both paths
+    out = {}
+    for sid, W, H, nS in [(9, 240, 135, 10), (8, 160, 160, 6)]:
+        sc = BuiltinScene(sid, earth if sid in (2, 9) else None)
+        r = Renderer(sc.desc)
+        rows = []
+        nbad = 0
+        for smp in range(nS):
+            cam = sc.camera(W, H, 1, 50)
+            want = np.zeros((H, W, 3))
+            st = A.oracle_stats()
+            oracle.oracle_render(sc.desc, C.byref(cam), smp, smp + 1, 1984, 1, 64, os.cpu_count(), want.ctypes.data, C.byref(st))
+            r.render(cam, smp, smp + 1)
+            got, _, gst = r.readback()
+            ok = (np.abs(got - want) <= 1e-3 * np.abs(want) + 1e-6).all(axis=2)
+            bad = np.argwhere(~ok)
+            nbad += len(bad)
+            for (j, i) in bad[:12]:
+                orec = np.zeros((64, 8))
+                n = oracle.oracle_trace_path(sc.desc, C.byref(cam), int(i), int(j), smp, 1984, orec.ctypes.data, 64)
+                grec = np.zeros((64, 8), np.float32)
+                p = A.rt_render_params(sample_begin=smp, sample_end=smp + 1, seed=1984, clear=1)
+                rc = r.lib.rt_debug_trace_path(r._h, C.byref(cam), C.byref(p), int(j * W + i), smp, grec.ctypes.data, 64)
+                assert rc == 0
+                g = []
+                for k in range(64):
+                    if grec[k, 7] == 0:
+                        break
+                    hid = int(grec[k, 0:1].view(np.uint32)[0])
+                    g.append({"hit_type": (hid >> 29) & 3, "hit_index": hid & 0x1fffffff, "t": float(grec[k, 1]),
+                              "mat": int(grec[k, 2:3].view(np.int32)[0]), "front": float(grec[k, 3]),
+                              "p": [float(x) for x in grec[k, 4:7]]})
+                o = [{"hit": orec[k, 0], "t": orec[k, 1], "mat": int(orec[k, 2]), "front": orec[k, 3],
+                      "p": list(orec[k, 4:7]), "mtype": int(orec[k, 7])} for k in range(n)]
+                rows.append({"pixel": [int(i), int(j)], "sample": smp, "gpu_rgb": [float(x) for x in got[j, i]],
+                             "oracle_rgb": [float(x) for x in want[j, i]], "gpu_path": g, "oracle_path": o})
+        r.close()
+        out[str(sid)] = {"W": W, "H": H, "samples": nS, "bad": nbad, "paths": rows}
+        print("scene", sid, "bad (pixel,sample) pairs:", nbad, "of", W * H * nS, flush=True)
+    with open(os.path.join(OUT, "probe_diverge.json"), "w") as f:
+        json.dump(out, f)
