@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--flags", type=lambda x: int(x, 0), default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -273,7 +274,7 @@ def run_b200_arm():
     accum = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)  # caller-owned accumulator (NCCL buffer)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     kw = dict(seed=SEED, stream=stream, accum_ptr=accum.data_ptr(), block_threads=ARGS.block_threads,
-              blocks_per_sm=ARGS.blocks_per_sm, variant=ARGS.variant)
+              blocks_per_sm=ARGS.blocks_per_sm, variant=ARGS.variant, flags=ARGS.flags)
 
     r = Renderer(sc.desc, device=local)
     info_desc_bytes = sc.desc_bytes()

@@ -48,7 +48,7 @@ namespace {
 
 using namespace rtdev;
 
-constexpr int kStackLevels = 32;
+constexpr int kMaxStackLevels = 32;
 constexpr int kTileW = 8, kTileH = 4;
 
 struct RenderArgs {
@@ -59,6 +59,7 @@ struct RenderArgs {
     uint32_t seed;
     int tilesX, tilesY;
     // test hook (STATS instantiations only): per-bounce records of one (pixel, sample) path
+    int stackLevels; // traversal stack entries per thread (BVH depth + 2, at most 32)
     int debugPixel, debugSample;
     float* debugOut; // [max_depth][8]: hit id, t, material, front, p.x, p.y, p.z, 1
     // byte sizes of the staged arrays (SMEM variant)
@@ -82,7 +83,7 @@ __global__ void RenderMega(const DevScene scene, const DevCamera cam, const Rend
 {
     extern __shared__ __align__(16) char smem[];
     const uint32_t smemBase = SmemAddr(smem);
-    uint32_t cursor = blockDim.x * 4u * kStackLevels;
+    uint32_t cursor = blockDim.x * 4u * (uint32_t)args.stackLevels;
 
     SceneView<SMEM> sv;
     if constexpr (SMEM) {
@@ -134,78 +135,88 @@ __global__ void RenderMega(const DevScene scene, const DevCamera cam, const Rend
         ray.o.x = ray.o.y = ray.o.z = 0.0;
         ray.d.x = ray.d.y = ray.d.z = 1.0;
         ray.time = 0.0f;
+        RaySlab slab = MakeSlab(ray);
+        double a = 3.0;
+        Trav tv;
+        tv.Begin(RT_TRAV_DONE);
+        tv.tMedium = 0.0;
         int sample = args.sampleBegin;
         int bounce = 0;
         bool alive = false;
         bool done = !valid;
 
+        // Lanes run a flat state machine.  Phase A (below): every lane shades the hit
+        // of its finished walk -- which either continues the path, or ends it and
+        // starts the pixel's next sample -- and leaves with a fresh ray.  Phase B:
+        // every lane walks the tree to completion.  (Leaving phase B early, once a
+        // number of lanes wait, was measured and is slower: profiles/README.md.)
         while (true) {
-            if (!alive && !done) {
-                if (sample >= args.sampleEnd) {
-                    done = true;
-                } else {
-                    DrawStream rng;
-                    rng.Begin(args.seed, pixel, (uint32_t)sample, 0u);
-                    ray = CameraRay(cam, i, j, rng);
-                    throughput = make_f3(1.0f, 1.0f, 1.0f);
-                    bounce = 0;
-                    alive = true;
-                    if (STATS) ++nPaths;
+            if (tv.ref == RT_TRAV_DONE && !done) {
+                if (alive) {
+                    ++nRays;
+                    if (tv.hit == RT_HIT_NONE) {
+                        sum = sum + throughput * background; // kernel.cu:74-79
+                        alive = false;
+                    } else {
+                        Hit h;
+                        FinalizeHit<FEAT, SMEM>(sv, ray, a, tv.hit, tv.t, tv.tMedium, h);
+                        const uint32_t type = RT_HIT_TYPE(tv.hit);
+                        if (STATS && args.debugOut && (int)pixel == args.debugPixel && sample == args.debugSample) {
+                            float* o = args.debugOut + bounce * 8;
+                            o[0] = __uint_as_float(tv.hit);
+                            o[1] = tv.t;
+                            o[2] = __int_as_float(h.material);
+                            o[3] = h.front ? 1.0f : 0.0f;
+                            o[4] = (float)h.p.x;
+                            o[5] = (float)h.p.y;
+                            o[6] = (float)h.p.z;
+                            o[7] = 1.0f;
+                        }
+                        const bool sphereLike = type == RT_LEAF_SPHERE || type == RT_LEAF_MOVING;
+                        DrawStream rng;
+                        rng.Begin(args.seed, pixel, (uint32_t)sample, (uint32_t)bounce + 1u);
+                        f3 atten, emitted;
+                        d3 dir;
+                        const bool scattered = Scatter<FEAT, SMEM>(sv, h, ray.d, a, sphereLike, rng, atten, dir, emitted);
+                        sum = sum + throughput * emitted; // kernel.cu:82-83
+                        if (!scattered) {
+                            alive = false;
+                        } else {
+                            throughput = throughput * atten; // kernel.cu:93-94
+                            ray.o = h.p;
+                            ray.d = dir;
+                            if (++bounce >= cam.max_depth) alive = false; // kernel.cu:71,97
+                        }
+                    }
+                    if (!alive) ++sample;
+                }
+                if (!alive) {
+                    if (sample >= args.sampleEnd) {
+                        done = true;
+                    } else {
+                        DrawStream rng;
+                        rng.Begin(args.seed, pixel, (uint32_t)sample, 0u);
+                        ray = CameraRay(cam, i, j, rng);
+                        throughput = make_f3(1.0f, 1.0f, 1.0f);
+                        bounce = 0;
+                        alive = true;
+                        if (STATS) ++nPaths;
+                    }
+                }
+                if (!done) {
+                    slab = MakeSlab(ray);
+                    a = fma(ray.d.x, ray.d.x, fma(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
+                    tv.Begin(sv.root_ref);
                 }
             }
             if (__all_sync(0xffffffffu, done)) break;
-            if (alive) {
+            while (tv.ref != RT_TRAV_DONE) {
                 uint32_t nodeTests = 0, primTests = 0;
-                const TraceResult tr = Trace<FEAT, SMEM>(sv, ray, 0.001f, stack, args.seed, pixel, (uint32_t)sample,
-                                                         (uint32_t)bounce + 1u, nodeTests, primTests);
-                ++nRays;
+                TraceStep<FEAT, SMEM>(sv, ray, slab, a, 0.001f, stack, tv, args.seed, pixel, (uint32_t)sample,
+                                      (uint32_t)bounce + 1u, nodeTests, primTests);
                 if (STATS) {
                     nNode += nodeTests;
                     nPrim += primTests;
-                }
-                if (tr.hit == RT_HIT_NONE) {
-                    // kernel.cu:74-79
-                    sum = sum + throughput * background;
-                    alive = false;
-                    ++sample;
-                } else {
-                    Hit h;
-                    FinalizeHit<FEAT, SMEM>(sv, ray, tr, h);
-                    const uint32_t type = RT_HIT_TYPE(tr.hit);
-                    if (STATS && args.debugOut && (int)pixel == args.debugPixel && sample == args.debugSample) {
-                        float* o = args.debugOut + bounce * 8;
-                        o[0] = __uint_as_float(tr.hit);
-                        o[1] = tr.t;
-                        o[2] = __int_as_float(h.material);
-                        o[3] = h.front ? 1.0f : 0.0f;
-                        o[4] = (float)h.p.x;
-                        o[5] = (float)h.p.y;
-                        o[6] = (float)h.p.z;
-                        o[7] = 1.0f;
-                    }
-                    const bool sphereLike = type == RT_LEAF_SPHERE || type == RT_LEAF_MOVING;
-                    DrawStream rng;
-                    rng.Begin(args.seed, pixel, (uint32_t)sample, (uint32_t)bounce + 1u);
-                    f3 atten, dir, emitted;
-                    const f3 dirIn = make_f3((float)ray.d.x, (float)ray.d.y, (float)ray.d.z);
-                    const bool scattered = Scatter<FEAT, SMEM>(sv, h, dirIn, sphereLike, rng, atten, dir, emitted);
-                    // kernel.cu:82-83
-                    sum = sum + throughput * emitted;
-                    if (!scattered) {
-                        alive = false;
-                        ++sample;
-                    } else {
-                        // kernel.cu:93-94
-                        throughput = throughput * atten;
-                        ray.o = h.p;
-                        ray.d.x = (double)dir.x;
-                        ray.d.y = (double)dir.y;
-                        ray.d.z = (double)dir.z;
-                        if (++bounce >= cam.max_depth) { // kernel.cu:71,97
-                            alive = false;
-                            ++sample;
-                        }
-                    }
                 }
             }
         }
@@ -530,7 +541,9 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     int threads = p->block_threads > 0 ? p->block_threads : 512;
     threads = std::max(32, std::min(1024, (threads / 32) * 32));
     int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;
-    const size_t stackBytes = (size_t)threads * 4 * kStackLevels;
+    const int stackLevels = std::max(2, std::min(kMaxStackLevels, h->host->max_depth + 2));
+    a.stackLevels = stackLevels;
+    const size_t stackBytes = (size_t)threads * 4 * stackLevels;
     const bool wantStats = (p->flags & 0x100) != 0 || a.debugOut != nullptr;
     const bool smem = !(p->flags & 0x200) && stackBytes + h->stagedBytes <= (size_t)h->maxSmemOptin / (size_t)blocksPerSm;
     const size_t smemBytes = stackBytes + (smem ? h->stagedBytes : 0);

@@ -88,19 +88,19 @@ struct RT_ALIGN(16) DevQuad {
 struct RT_ALIGN(16) DevMedium {
     uint32_t boundary_ref;  // leaf-style ref to the boundary primitives
     int32_t phase_material; // its Isotropic
-    float neg_inv_density;  // -1/rho
     int32_t medium_id;      // keys the RNG domain
     int32_t visits;         // reference-topology visit multiplicity (SURVEY trap T2)
-    int32_t _p[3];
+    double neg_inv_density; // -1/rho
+    double _p;
 };
 
 // ---- Material: 32 bytes.
 struct RT_ALIGN(16) DevMaterial {
     float r, g, b; // metal albedo, or the colour when `texture` < 0 (solid folded in)
-    float param;   // metal fuzz | dielectric index of refraction
+    float param;   // metal fuzz | dielectric index of refraction (fp32 copy)
     int32_t type;  // RT_MAT_*
     int32_t texture;
-    int32_t _p[2];
+    double param_d; // the same in FP64: it enters the scattered direction
 };
 
 // ---- Texture: 48 bytes.

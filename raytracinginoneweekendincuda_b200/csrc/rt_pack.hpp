@@ -522,8 +522,10 @@ struct Packer {
                 x.g = (float)m.albedo[1];
                 x.b = (float)m.albedo[2];
                 x.param = (float)m.fuzz;
+                x.param_d = m.fuzz;
             } else if (m.type == RT_MAT_DIELECTRIC) {
                 x.param = (float)m.ior;
+                x.param_d = m.ior;
             } else {
                 if (m.texture < 0 || m.texture >= d.n_textures) throw std::invalid_argument("material texture out of range");
                 const rt_texture& t = d.textures[m.texture];
@@ -610,7 +612,7 @@ struct Packer {
             std::memset(&dm, 0, sizeof dm);
             dm.boundary_ref = EmitRun(type, ids);
             dm.phase_material = ob.phase_material;
-            dm.neg_inv_density = (float)(-1.0 / ob.density);
+            dm.neg_inv_density = -1.0 / ob.density;
             dm.medium_id = ob.medium_id;
             dm.visits = 1;
             out.media.push_back(dm);

@@ -47,6 +47,43 @@ RT_DEV f3 cross(f3 a, f3 b) { return make_f3(a.y * b.z - a.z * b.y, a.z * b.x - 
 // Vec3.h:117-120 with :96-99: v * (1/len)
 RT_DEV f3 unit(f3 a) { return (1.0f / sqrtf(dot(a, a))) * a; }
 
+// FP64 vectors for the geometric chain hit point -> normal -> scattered
+// direction -> next hit point.  An fp32 link anywhere in that chain is a 6e-8
+// perturbation that diffuse inter-reflection between small spheres multiplies
+// by ~d/r per bounce and the marble texture by ~1e2 per unit of position
+// (measured: reference scene 9 loses parity after ~9 bounces inside its sphere
+// cluster), so the chain is FP64 end to end; B200 issues FP64 at half rate.
+RT_DEV d3 make_d3(double x, double y, double z)
+{
+    d3 r;
+    r.x = x;
+    r.y = y;
+    r.z = z;
+    return r;
+}
+RT_DEV d3 operator+(d3 a, d3 b) { return make_d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_DEV d3 operator-(d3 a, d3 b) { return make_d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_DEV d3 operator*(double s, d3 a) { return make_d3(s * a.x, s * a.y, s * a.z); }
+RT_DEV d3 operator-(d3 a) { return make_d3(-a.x, -a.y, -a.z); }
+RT_DEV double dot(d3 a, d3 b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
+RT_DEV f3 to_f3(d3 a) { return make_f3((float)a.x, (float)a.y, (float)a.z); }
+// 1/x, 1/sqrt(x), sqrt(x) to ~1e-14 relative from the fp32 SFU seed and one
+// (two for the reciprocal root) Newton steps: no FP64 division or root sequence.
+RT_DEV double RcpD(double x)
+{
+    const double r = (double)(1.0f / (float)x);
+    const double e = fma(-x, r, 1.0);
+    return fma(fma(e, e, e), r, r);
+}
+RT_DEV double RsqrtD(double x)
+{
+    double y = (double)rsqrtf((float)x);
+    const double e = fma(-x * y, y, 1.0); // 1 - x y^2
+    y = fma(y * e, fma(0.375, e, 0.5), y); // y (1 + e/2 + 3 e^2/8)
+    return y;
+}
+RT_DEV double SqrtD(double x) { return x > 1e-290 ? x * RsqrtD(x) : 0.0; }
+
 // ------------------------------------------------------------------ memory
 // Scene arrays are addressed either as 32-bit shared-memory addresses (SMEM)
 // or as generic pointers to global memory.
@@ -271,159 +308,99 @@ RT_DEV uint32_t HitRun(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, do
     return hit;
 }
 
-// ConstantMedium.h:52-94.  Two boundary queries, clip to [tmin,tmax], one
-// keyed uniform per visit.  `visits` > 1 reproduces the reference testing a
-// span-1 BVH leaf twice (SURVEY.md trap T2).  Returns the scatter t (always
-// >= tmin > 0) or RT_MISS.
-template <int FEAT, bool SMEM>
-RT_DEV float HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float tmin, float tmax,
-                       uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
-{
-    const float4 m0 = Ld4<SMEM>(sv.media, index * 32u);
-    const float4 m1 = Ld4<SMEM>(sv.media, index * 32u + 16u);
-    const uint32_t bref = (uint32_t)__float_as_int(m0.x);
-    const float negInvDensity = m0.z;
-    const uint32_t mediumId = (uint32_t)__float_as_int(m0.w);
-    const int visits = __float_as_int(m1.x);
-    const float big = 3.402823466e+38f;
-    float t1 = big;
-    if (HitRun<FEAT, SMEM>(sv, bref, r, a, -1.0e300, t1, primTests) == RT_HIT_NONE) return RT_MISS;
-    float t2 = big;
-    if (HitRun<FEAT, SMEM>(sv, bref, r, a, (double)t1 + 0.0001, t2, primTests) == RT_HIT_NONE) return RT_MISS;
-    const float rayLength = sqrtf((float)a);
-    float best = RT_MISS;
-    for (int v = 0; v < visits; ++v) {
-        float e1 = t1, e2 = t2;
-        if (e1 < tmin) e1 = tmin;
-        if (e2 > tmax) e2 = tmax;
-        if (e1 >= e2) break;
-        if (e1 < 0.0f) e1 = 0.0f;
-        const float inside = (e2 - e1) * rayLength;
-        const rt_u4 k = rt_rng_block(seed, pixel, sample, slot, 1u + 2u * mediumId + (uint32_t)v, 0);
-        const float hitDistance = negInvDensity * logf(rt_bits_to_u01(k.x));
-        if (hitDistance > inside) continue;
-        best = e1 + hitDistance / rayLength;
-        tmax = best;
-    }
-    return best;
-}
-
-// ---------------------------------------------------------------- traversal
-// BvhNode.h:101-158 re-designed: children boxes are fetched as one 64-byte
-// pair and tested together, the nearer child is entered first and the other
-// pushed, leaves are contiguous typed runs.  The closest hit is the same
-// minimum over all primitives the reference computes (its order of visiting
-// them does not matter: media draws are keyed, not sequential).
-struct TraceResult {
-    uint32_t hit; // RT_HIT_* id or RT_HIT_NONE
-    float t;
-};
-
-template <int FEAT, bool SMEM>
-RT_DEV TraceResult Trace(const SceneView<SMEM>& sv, const Ray& r, float tmin, const Stack& stack, uint32_t seed,
-                         uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& nodeTests, uint32_t& primTests)
-{
-    const RaySlab slab = MakeSlab(r);
-    const double a = fma(r.d.x, r.d.x, fma(r.d.y, r.d.y, r.d.z * r.d.z));
-    TraceResult res;
-    res.hit = RT_HIT_NONE;
-    res.t = 3.402823466e+38f;
-    uint32_t ref = sv.root_ref;
-    int sp = 0;
-    while (true) {
-        if (!(ref & RT_REF_LEAF)) {
-            const uint32_t off = ref * 32u;
-            const float4 lo0 = Ld4<SMEM>(sv.nodes, off);
-            const float4 hi0 = Ld4<SMEM>(sv.nodes, off + 16u);
-            const float4 lo1 = Ld4<SMEM>(sv.nodes, off + 32u);
-            const float4 hi1 = Ld4<SMEM>(sv.nodes, off + 48u);
-            nodeTests += 2;
-            const float e0 = SlabEntry(lo0, hi0, slab, tmin, res.t);
-            const float e1 = SlabEntry(lo1, hi1, slab, tmin, res.t);
-            const uint32_t r0 = (uint32_t)__float_as_int(lo0.w), r1 = (uint32_t)__float_as_int(lo1.w);
-            const bool h0 = e0 < 3.0e38f, h1 = e1 < 3.0e38f;
-            if (h0 && h1) {
-                const bool swap = e1 < e0;
-                stack.Push(sp++, swap ? r0 : r1);
-                ref = swap ? r1 : r0;
-                continue;
-            }
-            if (h0 || h1) {
-                ref = h0 ? r0 : r1;
-                continue;
-            }
-        } else {
-            if ((FEAT & RT_FEAT_MEDIUM) && RT_REF_TYPE(ref) == RT_LEAF_MEDIUM) {
-                const uint32_t m = RT_REF_FIRST(ref);
-                const float t = HitMedium<FEAT, SMEM>(sv, m, r, a, tmin, res.t, seed, pixel, sample, slot, primTests);
-                if (t != RT_MISS) {
-                    res.t = t;
-                    res.hit = RT_HIT_MAKE(RT_LEAF_MEDIUM, m);
-                }
-            } else {
-                const uint32_t h = HitRun<FEAT, SMEM>(sv, ref, r, a, (double)tmin, res.t, primTests);
-                if (h != RT_HIT_NONE) res.hit = h;
-            }
-        }
-        if (sp == 0) break;
-        ref = stack.Pop(--sp);
-    }
-    return res;
-}
-
 // ------------------------------------------------------------ hit records
 // Hittable.h:11-31, filled for the winning primitive only.
 struct Hit {
     d3 p;          // FP64 hit point
-    f3 n;          // shading normal (faces the ray)
-    f3 outward;    // geometric outward normal (sphere UV)
+    d3 n;          // FP64 shading normal (faces the ray)
+    f3 outward;    // geometric outward normal, fp32 copy (sphere UV)
     float u, v;    // quad: alpha, beta; sphere: filled on demand
     bool front;
     int32_t material;
 };
 
-RT_DEV void SetFaceNormal(Hit& h, f3 dir, f3 outward)
+RT_DEV void SetFaceNormal(Hit& h, const d3& dir, const d3& outward) // Hittable.h:26-30
 {
-    h.front = dot(dir, outward) < 0.0f;
+    h.front = dot(dir, outward) < 0.0;
     h.n = h.front ? outward : -outward;
-    h.outward = outward;
+    h.outward = to_f3(outward);
 }
 
-// Re-solves the winning sphere in FP64: one Newton step on
-// f(t) = a t^2 + 2 b t + c from the fp32 root puts the hit point on the sphere
-// to ~1e-15 relative, so the normal (P-C)/r is as good as fp32 can hold.
-RT_DEV void FinalizeSphereAt(d3 c, double radius, const Ray& r, float t, Hit& h)
+// The fp32 root of a sphere re-solved in FP64: one Newton step on
+// f(t) = a t^2 + 2 b t + c puts the hit point on the sphere to ~1e-14 relative.
+RT_DEV double RefineSphereT(d3 c, double radius, const Ray& r, double a, float t)
 {
     const double ocx = r.o.x - c.x, ocy = r.o.y - c.y, ocz = r.o.z - c.z;
-    const double a = fma(r.d.x, r.d.x, fma(r.d.y, r.d.y, r.d.z * r.d.z));
     const double b = fma(ocx, r.d.x, fma(ocy, r.d.y, ocz * r.d.z));
     const double cc = fma(ocx, ocx, fma(ocy, ocy, fma(ocz, ocz, -radius * radius)));
-    double td = (double)t;
+    const double td = (double)t;
     const double f = fma(fma(a, td, 2.0 * b), td, cc);
     const double fp = 2.0 * fma(a, td, b);
-    td -= (double)((float)f / (float)fp);
+    return td - (double)((float)f / (float)fp);
+}
+
+// t = (D - n.O)/(n.d) of a quad refined once in FP64 (Quad.h:62).
+template <bool SMEM> RT_DEV double RefineQuadT(const SceneView<SMEM>& sv, uint32_t index, const Ray& r)
+{
+    const uint32_t off = index * 96u;
+    const double2 q1 = LdD2<SMEM>(sv.quads, off + 16u);
+    const double2 q2 = LdD2<SMEM>(sv.quads, off + 32u);
+    const double nz = LdD2<SMEM>(sv.quads, off + 48u).x;
+    const double denom = fma(q2.x, r.d.x, fma(q2.y, r.d.y, nz * r.d.z));
+    const double num = q1.y - fma(q2.x, r.o.x, fma(q2.y, r.o.y, nz * r.o.z));
+    const float invDen = 1.0f / (float)denom;
+    double td = (double)((float)num * invDen);
+    td += (double)((float)fma(-td, denom, num) * invDen);
+    td += (double)((float)fma(-td, denom, num) * invDen);
+    return td;
+}
+
+template <bool SMEM> RT_DEV d3 SphereCentre(const SceneView<SMEM>& sv, uint32_t index, double& radius)
+{
+    const double2 s0 = LdD2<SMEM>(sv.spheres, index * 32u);
+    const double2 s1 = LdD2<SMEM>(sv.spheres, index * 32u + 16u);
+    radius = s1.y;
+    return make_d3(s0.x, s0.y, s1.x);
+}
+
+// FP64 distance of a surface hit found by HitRun (hit id + fp32 t).
+template <int FEAT, bool SMEM> RT_DEV double RefineT(const SceneView<SMEM>& sv, uint32_t hit, const Ray& r, double a, float t)
+{
+    const uint32_t type = RT_HIT_TYPE(hit), index = RT_HIT_INDEX(hit);
+    if ((FEAT & RT_FEAT_QUAD) && type == RT_LEAF_QUAD) return RefineQuadT<SMEM>(sv, index, r);
+    double radius;
+    d3 c;
+    if ((FEAT & RT_FEAT_MOVING) && type == RT_LEAF_MOVING)
+        c = MovingCentre<SMEM>(sv, index, r.time, radius);
+    else
+        c = SphereCentre<SMEM>(sv, index, radius);
+    return RefineSphereT(c, radius, r, a, t);
+}
+
+RT_DEV void FinalizeSphereAt(d3 c, double radius, const Ray& r, double a, float t, Hit& h)
+{
+    const double td = RefineSphereT(c, radius, r, a, t);
     h.p.x = fma(td, r.d.x, r.o.x);
     h.p.y = fma(td, r.d.y, r.o.y);
     h.p.z = fma(td, r.d.z, r.o.z);
-    const float invR = 1.0f / (float)radius;
-    const f3 outward = make_f3((float)(h.p.x - c.x) * invR, (float)(h.p.y - c.y) * invR, (float)(h.p.z - c.z) * invR);
-    SetFaceNormal(h, make_f3((float)r.d.x, (float)r.d.y, (float)r.d.z), outward);
+    const double invR = RcpD(radius); // Sphere.h:54 with Vec3.h:96-99: (P - C) * (1/r)
+    SetFaceNormal(h, r.d, invR * (h.p - c));
 }
 
-template <int FEAT, bool SMEM> RT_DEV void FinalizeHit(const SceneView<SMEM>& sv, const Ray& r, const TraceResult& tr, Hit& h)
+template <int FEAT, bool SMEM>
+RT_DEV void FinalizeHit(const SceneView<SMEM>& sv, const Ray& r, double a, uint32_t hit, float t, double tMedium, Hit& h)
 {
-    const uint32_t type = RT_HIT_TYPE(tr.hit), index = RT_HIT_INDEX(tr.hit);
+    const uint32_t type = RT_HIT_TYPE(hit), index = RT_HIT_INDEX(hit);
     h.u = 0.0f;
     h.v = 0.0f;
     if ((FEAT & RT_FEAT_MEDIUM) && type == RT_LEAF_MEDIUM) {
         // ConstantMedium.h:86-91: arbitrary normal, front face, phase material
         const float4 m0 = Ld4<SMEM>(sv.media, index * 32u);
-        const double td = (double)tr.t;
-        h.p.x = fma(td, r.d.x, r.o.x);
-        h.p.y = fma(td, r.d.y, r.o.y);
-        h.p.z = fma(td, r.d.z, r.o.z);
-        h.n = make_f3(1.0f, 0.0f, 0.0f);
-        h.outward = h.n;
+        h.p.x = fma(tMedium, r.d.x, r.o.x);
+        h.p.y = fma(tMedium, r.d.y, r.o.y);
+        h.p.z = fma(tMedium, r.d.z, r.o.z);
+        h.n = make_d3(1.0, 0.0, 0.0);
+        h.outward = make_f3(1.0f, 0.0f, 0.0f);
         h.front = true;
         h.material = __float_as_int(m0.y);
     } else if ((FEAT & RT_FEAT_QUAD) && type == RT_LEAF_QUAD) {
@@ -434,12 +411,7 @@ template <int FEAT, bool SMEM> RT_DEV void FinalizeHit(const SceneView<SMEM>& sv
         const double2 q3 = LdD2<SMEM>(sv.quads, off + 48u);
         const float4 q4 = Ld4<SMEM>(sv.quads, off + 64u);
         const float4 q5 = Ld4<SMEM>(sv.quads, off + 80u);
-        const double nz = q3.x;
-        const double denom = fma(q2.x, r.d.x, fma(q2.y, r.d.y, nz * r.d.z));
-        const double num = q1.y - fma(q2.x, r.o.x, fma(q2.y, r.o.y, nz * r.o.z));
-        // division refined once in FP64: t = t0 + (num - t0*denom)/denom
-        double td = (double)((float)num / (float)denom);
-        td += (double)((float)fma(-td, denom, num) / (float)denom);
+        const double td = RefineQuadT<SMEM>(sv, index, r);
         h.p.x = fma(td, r.d.x, r.o.x);
         h.p.y = fma(td, r.d.y, r.o.y);
         h.p.z = fma(td, r.d.z, r.o.z);
@@ -450,22 +422,136 @@ template <int FEAT, bool SMEM> RT_DEV void FinalizeHit(const SceneView<SMEM>& sv
         h.u = dot(w, cross(planar, v));
         h.v = dot(w, cross(u, planar));
         h.material = __float_as_int(q5.w);
-        SetFaceNormal(h, make_f3((float)r.d.x, (float)r.d.y, (float)r.d.z), make_f3((float)q2.x, (float)q2.y, (float)nz));
+        SetFaceNormal(h, r.d, make_d3(q2.x, q2.y, q3.x));
     } else if ((FEAT & RT_FEAT_MOVING) && type == RT_LEAF_MOVING) {
         double radius;
         const d3 c = MovingCentre<SMEM>(sv, index, r.time, radius);
-        FinalizeSphereAt(c, radius, r, tr.t, h);
+        FinalizeSphereAt(c, radius, r, a, t, h);
         h.material = __double2hiint(LdD2<SMEM>(sv.moving, index * 64u + 16u).y);
     } else {
-        const double2 s0 = LdD2<SMEM>(sv.spheres, index * 32u);
-        const double2 s1 = LdD2<SMEM>(sv.spheres, index * 32u + 16u);
-        d3 c;
-        c.x = s0.x;
-        c.y = s0.y;
-        c.z = s1.x;
-        FinalizeSphereAt(c, s1.y, r, tr.t, h);
+        double radius;
+        const d3 c = SphereCentre<SMEM>(sv, index, radius);
+        FinalizeSphereAt(c, radius, r, a, t, h);
         h.material = LdI<SMEM>(sv.sphere_material, index * 4u);
     }
+}
+
+// ---------------------------------------------------------------- media
+// ConstantMedium.h:52-94.  Two boundary queries, clip to [tmin,tmax], one
+// keyed uniform per visit.  `visits` > 1 reproduces the reference testing a
+// span-1 BVH leaf twice (SURVEY.md trap T2).  Distances are FP64: the scatter
+// point is the origin of the rest of the path.  Returns true with the scatter
+// distance in tOut (always >= tmin > 0).
+template <int FEAT, bool SMEM>
+RT_DEV bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float tminF, float tmaxF,
+                      uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests, double& tOut)
+{
+    const float4 m0 = Ld4<SMEM>(sv.media, index * 32u);
+    const uint32_t bref = (uint32_t)__float_as_int(m0.x);
+    const uint32_t mediumId = (uint32_t)__float_as_int(m0.z);
+    const int visits = __float_as_int(m0.w);
+    const float big = 3.402823466e+38f;
+    float t1f = big;
+    const uint32_t h1 = HitRun<FEAT, SMEM>(sv, bref, r, a, -1.0e300, t1f, primTests);
+    if (h1 == RT_HIT_NONE) return false;
+    const double t1 = RefineT<FEAT, SMEM>(sv, h1, r, a, t1f);
+    float t2f = big;
+    // the candidates of the second query are fp32 roots: the entry root must not pass
+    // as "beyond t1 + 1e-4" because its fp32 value lies above the refined t1
+    const uint32_t h2 = HitRun<FEAT, SMEM>(sv, bref, r, a, fmax(t1, (double)t1f) + 0.0001, t2f, primTests);
+    if (h2 == RT_HIT_NONE) return false;
+    const double t2 = RefineT<FEAT, SMEM>(sv, h2, r, a, t2f);
+    const double negInvDensity = LdD2<SMEM>(sv.media, index * 32u + 16u).x;
+    const double invLength = RsqrtD(a), rayLength = a * invLength;
+    double tmax = (double)tmaxF;
+    bool any = false;
+    for (int v = 0; v < visits; ++v) {
+        double e1 = t1, e2 = t2;
+        if (e1 < (double)tminF) e1 = (double)tminF;
+        if (e2 > tmax) e2 = tmax;
+        if (e1 >= e2) break;
+        if (e1 < 0.0) e1 = 0.0;
+        const double inside = (e2 - e1) * rayLength;
+        const rt_u4 k = rt_rng_block(seed, pixel, sample, slot, 1u + 2u * mediumId + (uint32_t)v, 0);
+        // ConstantMedium.h:79: log() of a float is the fp32 logarithm; taken here as
+        // the correctly rounded one
+        const double hitDistance = negInvDensity * (double)(float)log((double)rt_bits_to_u01(k.x));
+        if (hitDistance > inside) continue;
+        tmax = e1 + hitDistance * invLength;
+        any = true;
+    }
+    tOut = tmax;
+    return any;
+}
+
+// ---------------------------------------------------------------- traversal
+// BvhNode.h:101-158 re-designed: children boxes are fetched as one 64-byte
+// pair and tested together, the nearer child is entered first and the other
+// pushed, leaves are contiguous typed runs.  The closest hit is the same
+// minimum over all primitives the reference computes (its order of visiting
+// them does not matter: media draws are keyed, not sequential).
+//
+// Traversal is a resumable state machine -- one node (or one leaf) per Step --
+// so that the kernel can interleave lanes that are still walking the tree with
+// lanes that are shading or starting a new path.
+#define RT_TRAV_DONE 0xffffffffu
+struct Trav {
+    uint32_t ref; // node / leaf to visit next, RT_TRAV_DONE when the walk is over
+    int sp;
+    float t;      // closest hit so far (fp32; refined by FinalizeHit)
+    uint32_t hit; // RT_HIT_* id or RT_HIT_NONE
+    double tMedium; // FP64 scatter distance when `hit` is a medium
+    RT_DEV void Begin(uint32_t root)
+    {
+        ref = root;
+        sp = 0;
+        t = 3.402823466e+38f;
+        hit = RT_HIT_NONE;
+    }
+};
+
+template <int FEAT, bool SMEM>
+RT_DEV void TraceStep(const SceneView<SMEM>& sv, const Ray& r, const RaySlab& slab, double a, float tmin, const Stack& stack,
+                      Trav& tv, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& nodeTests,
+                      uint32_t& primTests)
+{
+    const uint32_t ref = tv.ref;
+    if (!(ref & RT_REF_LEAF)) {
+        const uint32_t off = ref * 32u;
+        const float4 lo0 = Ld4<SMEM>(sv.nodes, off);
+        const float4 hi0 = Ld4<SMEM>(sv.nodes, off + 16u);
+        const float4 lo1 = Ld4<SMEM>(sv.nodes, off + 32u);
+        const float4 hi1 = Ld4<SMEM>(sv.nodes, off + 48u);
+        nodeTests += 2;
+        const float e0 = SlabEntry(lo0, hi0, slab, tmin, tv.t);
+        const float e1 = SlabEntry(lo1, hi1, slab, tmin, tv.t);
+        const uint32_t r0 = (uint32_t)__float_as_int(lo0.w), r1 = (uint32_t)__float_as_int(lo1.w);
+        const bool h0 = e0 < 3.0e38f, h1 = e1 < 3.0e38f;
+        if (h0 && h1) {
+            const bool swap = e1 < e0;
+            stack.Push(tv.sp++, swap ? r0 : r1);
+            tv.ref = swap ? r1 : r0;
+            return;
+        }
+        if (h0 || h1) {
+            tv.ref = h0 ? r0 : r1;
+            return;
+        }
+    } else {
+        if ((FEAT & RT_FEAT_MEDIUM) && RT_REF_TYPE(ref) == RT_LEAF_MEDIUM) {
+            const uint32_t m = RT_REF_FIRST(ref);
+            double tm;
+            if (HitMedium<FEAT, SMEM>(sv, m, r, a, tmin, tv.t, seed, pixel, sample, slot, primTests, tm)) {
+                tv.t = (float)tm;
+                tv.tMedium = tm;
+                tv.hit = RT_HIT_MAKE(RT_LEAF_MEDIUM, m);
+            }
+        } else {
+            const uint32_t h = HitRun<FEAT, SMEM>(sv, ref, r, a, (double)tmin, tv.t, primTests);
+            if (h != RT_HIT_NONE) tv.hit = h;
+        }
+    }
+    tv.ref = tv.sp == 0 ? RT_TRAV_DONE : stack.Pop(--tv.sp);
 }
 
 // ----------------------------------------------------------------- textures
@@ -551,8 +637,11 @@ template <bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv, int tex, 
         }
         // Texture.h:159-165: marble
         const DevPerlin* pt = &sv.perlins[__ldg(&t->index)];
-        const float phase = (float)((double)__ldg(&t->scale) * h.p.z) + 10.0f * PerlinTurb(pt, h.p, 7);
-        const float g = 0.5f * (1.0f + sinf(phase));
+        // the phase is ~scale*z (tens of radians): reduce it mod 2 pi in FP64, then sinf
+        const double phase = fma((double)__ldg(&t->scale), h.p.z, 10.0 * (double)PerlinTurb(pt, h.p, 7));
+        const double k = rint(phase * 0.15915494309189535);
+        const float red = (float)fma(-k, 1.2246467991473532e-16 * 2.0, fma(-k, 6.283185307179586, phase));
+        const float g = 0.5f * (1.0f + sinf(red));
         return make_f3(g, g, g);
     }
     return make_f3(0.0f, 0.0f, 0.0f);
@@ -579,73 +668,81 @@ struct DrawStream {
     }
 };
 
-// Material.h:14-24
-RT_DEV f3 RandomInUnitSphere(DrawStream& rng)
+// Material.h:14-24.  The candidate is exact in FP64 (2x-1 of a 24-bit x); the
+// rejection test is decided in fp32 unless it is within rounding of the sphere.
+RT_DEV d3 RandomInUnitSphere(DrawStream& rng)
 {
-    f3 p;
-    do {
+    while (true) {
         const float x = rng.Next();
         const float y = rng.Next();
         const float z = rng.Next();
-        p = make_f3(2.0f * x - 1.0f, 2.0f * y - 1.0f, 2.0f * z - 1.0f);
-    } while (dot(p, p) >= 1.0f);
-    return p;
+        const float fx = 2.0f * x - 1.0f, fy = 2.0f * y - 1.0f, fz = 2.0f * z - 1.0f;
+        const float l2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+        if (l2 >= 1.00001f) continue;
+        const d3 p = make_d3(fma(2.0, (double)x, -1.0), fma(2.0, (double)y, -1.0), fma(2.0, (double)z, -1.0));
+        if (l2 > 0.99999f && dot(p, p) >= 1.0) continue;
+        return p;
+    }
 }
 
-RT_DEV f3 Reflect(f3 v, f3 n) { return v - (2.0f * dot(v, n)) * n; } // Vec3.h:122-125
+RT_DEV d3 Reflect(d3 v, d3 n) { return v - (2.0 * dot(v, n)) * n; } // Vec3.h:122-125
 
 // Returns false when the path ends (light, or absorbed by metal).  On true,
 // `dir` is the scattered direction (not normalised, like the reference) and
 // `atten` the attenuation.  `emitted` is Material::Emitted (black unless light).
+// `a` = |dirIn|^2.
 template <int FEAT, bool SMEM>
-RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, f3 dirIn, bool sphereLike, DrawStream& rng, f3& atten, f3& dir,
-                    f3& emitted)
+RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, const d3& dirIn, double a, bool sphereLike, DrawStream& rng,
+                    f3& atten, d3& dir, f3& emitted)
 {
     const float4 m0 = Ld4<SMEM>(sv.materials, (uint32_t)h.material * 32u);
     const float4 m1 = Ld4<SMEM>(sv.materials, (uint32_t)h.material * 32u + 16u);
     const int type = __float_as_int(m1.x);
     const int tex = __float_as_int(m1.y);
+    const double param = __hiloint2double(__float_as_int(m1.w), __float_as_int(m1.z)); // fuzz | ior, FP64
     emitted = make_f3(0.0f, 0.0f, 0.0f);
     f3 colour = make_f3(m0.x, m0.y, m0.z);
     if ((FEAT & RT_FEAT_TEXTURE) && tex >= 0 && type != RT_MAT_METAL && type != RT_MAT_DIELECTRIC)
         colour = TextureValue<SMEM>(sv, tex, h, sphereLike);
     if (type == RT_MAT_LAMBERTIAN) { // Material.h:68-86
         dir = h.n + RandomInUnitSphere(rng);
-        if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = h.n;
+        if (fabs(dir.x) < 1e-8 && fabs(dir.y) < 1e-8 && fabs(dir.z) < 1e-8) dir = h.n;
         atten = colour;
         return true;
     }
     if (type == RT_MAT_METAL) { // Metal.h:18-30 (draws even when fuzz == 0)
-        const f3 reflected = Reflect(unit(dirIn), h.n);
-        dir = reflected + m0.w * RandomInUnitSphere(rng);
+        const d3 reflected = Reflect(RsqrtD(a) * dirIn, h.n);
+        dir = reflected + param * RandomInUnitSphere(rng);
         atten = colour;
-        return dot(dir, h.n) > 0.0f;
+        return dot(dir, h.n) > 0.0;
     }
     if (type == RT_MAT_DIELECTRIC) { // Dielectric.h:18-68, Vec3.h:127-141
         atten = make_f3(1.0f, 1.0f, 1.0f);
-        const float ratio = h.front ? 1.0f / m0.w : m0.w;
-        const f3 ud = unit(dirIn);
-        const float cosTheta = fminf(dot(-ud, h.n), 1.0f);
-        const float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
-        bool reflect = ratio * sinTheta > 1.0f;
+        const double ratio = h.front ? RcpD(param) : param;
+        const d3 ud = RsqrtD(a) * dirIn;
+        const double cosTheta = fmin(-dot(ud, h.n), 1.0);
+        const float cosF = (float)cosTheta, ratioF = (float)ratio;
+        const float sinTheta = sqrtf(1.0f - cosF * cosF);
+        bool reflect = ratioF * sinTheta > 1.0f;
         if (!reflect) { // no draw on total internal reflection
-            float r0 = (1.0f - ratio) / (1.0f + ratio);
+            float r0 = (1.0f - ratioF) / (1.0f + ratioF);
             r0 = r0 * r0;
-            const float k = 1.0f - cosTheta;
+            const float k = 1.0f - cosF;
             const float k2 = k * k;
             reflect = r0 + (1.0f - r0) * (k2 * k2 * k) > rng.Next();
         }
         if (reflect) {
             dir = Reflect(ud, h.n);
         } else {
-            const f3 perp = ratio * (ud + cosTheta * h.n);
-            const f3 para = -sqrtf(fabsf(1.0f - dot(perp, perp))) * h.n;
+            const d3 perp = ratio * (ud + cosTheta * h.n);
+            const d3 para = -SqrtD(fabs(1.0 - dot(perp, perp))) * h.n;
             dir = perp + para;
         }
         return true;
     }
     if (type == RT_MAT_ISOTROPIC) { // Material.h:151-162
-        dir = unit(RandomInUnitSphere(rng));
+        const d3 p = RandomInUnitSphere(rng);
+        dir = RsqrtD(dot(p, p)) * p;
         atten = colour;
         return true;
     }

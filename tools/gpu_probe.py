@@ -135,6 +135,24 @@ if "dump9" in what:
     np.savez_compressed(os.path.join(OUT, "dump_scene9.npz"), gpu=got, oracle=want / spp)
     print("dumped scene 9")
 
+if "sweep" in what:
+    rows = []
+    sc = BuiltinScene(10)
+    cam = sc.camera(3840, 2160, 16, 50)
+    r = Renderer(sc.desc)
+    for threads, bps in [(512, 1), (256, 2), (128, 4), (128, 5), (128, 6), (256, 3), (64, 10), (384, 2), (1024, 1)]:
+        for refill in (32, 24, 16, 12, 8, 4, 1):
+            try:
+                ms, st = timed(r, cam, reps=2, block_threads=threads, blocks_per_sm=bps, flags=refill << 16)
+            except Exception as e:  # noqa: BLE001
+                print("skip", threads, bps, refill, str(e)[:80])
+                break
+            rows.append({"threads": threads, "blocks_per_sm": bps, "refill": refill, "ms": ms, "grays_s": st.rays / ms / 1e6})
+            print(rows[-1], flush=True)
+    r.close()
+    with open(os.path.join(OUT, "probe_sweep.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+
 if "diverge" in what:
     # per-sample comparison: find (pixel, sample) paths whose radiance differs, dump both paths
     out = {}
