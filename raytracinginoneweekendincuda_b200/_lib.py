@@ -11,7 +11,8 @@ _LIB = None
 
 
 def library_path() -> str:
-    return os.path.join(_PKG, "librt_b200.so")
+    # RT_B200_LIBRARY: development override (e.g. a build with other compiler flags)
+    return os.environ.get("RT_B200_LIBRARY") or os.path.join(_PKG, "librt_b200.so")
 
 
 def load_library() -> C.CDLL:

@@ -59,6 +59,7 @@ struct RenderArgs {
     uint32_t seed;
     int tilesX, tilesY;
     // test hook (STATS instantiations only): per-bounce records of one (pixel, sample) path
+    int waveSlots, waveIdleExit, waveLeafBatch, waveRefillMin; // wavefront variant tuning
     int stackLevels; // traversal stack entries per thread (BVH depth + 2, at most 32)
     int debugPixel, debugSample;
     float* debugOut; // [max_depth][8]: hit id, t, material, front, p.x, p.y, p.z, 1
@@ -78,13 +79,11 @@ __device__ __forceinline__ uint32_t Stage(uint32_t& cursor, char* smem, const vo
     return at;
 }
 
-template <int FEAT, bool SMEM, bool STATS>
-__global__ void RenderMega(const DevScene scene, const DevCamera cam, const RenderArgs args)
+// Stages the scene arrays in shared memory (SMEM) or points at them in global memory.
+template <bool SMEM>
+__device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, const RenderArgs& args, char* smem, uint32_t smemBase,
+                                                      uint32_t& cursor)
 {
-    extern __shared__ __align__(16) char smem[];
-    const uint32_t smemBase = SmemAddr(smem);
-    uint32_t cursor = blockDim.x * 4u * (uint32_t)args.stackLevels;
-
     SceneView<SMEM> sv;
     if constexpr (SMEM) {
         sv.nodes.a = smemBase + Stage(cursor, smem, scene.nodes, args.nodesBytes);
@@ -108,6 +107,24 @@ __global__ void RenderMega(const DevScene scene, const DevCamera cam, const Rend
     sv.perlins = scene.perlins;
     sv.images = scene.images;
     sv.root_ref = scene.root_ref;
+
+    return sv;
+}
+
+// 768 threads per SM (24 warps, 80 registers): measured 18 % faster than 512 x 87
+// registers -- the kernel stalls on fixed-latency dependencies ("wait"), which more
+// resident warps hide (profiles/README.md).
+// The feature-complete instantiations need ~125 registers and stay at 512.
+constexpr int MegaMaxThreads(int feat) { return feat == 0 ? 768 : 512; }
+
+template <int FEAT, bool SMEM, bool STATS>
+__global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderMega(const DevScene scene, const DevCamera cam, const RenderArgs args)
+{
+    extern __shared__ __align__(16) char smem[];
+    const uint32_t smemBase = SmemAddr(smem);
+    uint32_t cursor = blockDim.x * 4u * (uint32_t)args.stackLevels;
+
+    const SceneView<SMEM> sv = SetupScene<SMEM>(scene, args, smem, smemBase, cursor);
 
     Stack stack;
     stack.base = smemBase + threadIdx.x * 4u;
@@ -173,8 +190,7 @@ __global__ void RenderMega(const DevScene scene, const DevCamera cam, const Rend
                             o[7] = 1.0f;
                         }
                         const bool sphereLike = type == RT_LEAF_SPHERE || type == RT_LEAF_MOVING;
-                        DrawStream rng;
-                        rng.Begin(args.seed, pixel, (uint32_t)sample, (uint32_t)bounce + 1u);
+                        const StreamKey rng = MakeKey(args.seed, pixel, (uint32_t)sample, (uint32_t)bounce + 1u);
                         f3 atten, emitted;
                         d3 dir;
                         const bool scattered = Scatter<FEAT, SMEM>(sv, h, ray.d, a, sphereLike, rng, atten, dir, emitted);
@@ -194,8 +210,7 @@ __global__ void RenderMega(const DevScene scene, const DevCamera cam, const Rend
                     if (sample >= args.sampleEnd) {
                         done = true;
                     } else {
-                        DrawStream rng;
-                        rng.Begin(args.seed, pixel, (uint32_t)sample, 0u);
+                        const StreamKey rng = MakeKey(args.seed, pixel, (uint32_t)sample, 0u);
                         ray = CameraRay(cam, i, j, rng);
                         throughput = make_f3(1.0f, 1.0f, 1.0f);
                         bounce = 0;
@@ -235,6 +250,336 @@ __global__ void RenderMega(const DevScene scene, const DevCamera cam, const Rend
             nPaths += __shfl_down_sync(0xffffffffu, nPaths, off);
             nNode += __shfl_down_sync(0xffffffffu, nNode, off);
             nPrim += __shfl_down_sync(0xffffffffu, nPrim, off);
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&args.stats[0], nRays);
+        if (STATS) {
+            atomicAdd(&args.stats[1], nPaths);
+            atomicAdd(&args.stats[2], nNode);
+            atomicAdd(&args.stats[3], nPrim);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Wavefront variant, on chip.  The classic wavefront path tracer (ray-gen /
+// extend / shade kernels exchanging rays through queues in device memory) would
+// move ~200 B per ray through HBM -- 4 TB/s at 20 Grays/s -- for a scene that
+// fits in shared memory.  Here the queues live in shared memory and belong to a
+// warp: each warp owns a tile of 8 x S/8 pixels = S path slots (S = 64..128; SoA, 99 B each) and
+// three compacted slot lists built with ballot + popc prefix sums:
+//   ready  paths that have a ray to extend
+//   shade  paths whose ray hit a surface (or a medium)
+//   gen    paths that ended (miss / absorbed / light / depth) and need the
+//          pixel's next camera sample
+// and alternates three phases, each run by 32 lanes taking 32 list entries:
+//   EXTEND  lanes pull slots off `ready` the moment they fall idle (persistent
+//           threads over the warp's own queue), so box tests run on a full warp
+//           while `ready` lasts; a lane that reaches a leaf waits until enough
+//           lanes hold one, then the FP64 primitive tests run together;
+//   SHADE   FinalizeHit + Scatter for 32 hits at a time;
+//   GEN     background / next sample / camera ray for 32 ended paths at a time.
+// A lane is no longer tied to a pixel, only a slot is: samples of a pixel are
+// still taken in order and summed in the slot, so the image is bit-identical to
+// the megakernel's.
+#define RT_HIT_GEN_FIRST 0xfffffffeu /* slot has not started its first sample */
+#define RT_HIT_GEN_ENDED 0xfffffffdu /* path ended on a surface                */
+
+// One warp's pool: S path slots, structure of arrays (field stride = S), 88 B per
+// slot, then the three slot lists.
+struct Pool {
+    double* O;     // [3][S] ray origin
+    double* D;     // [3][S] ray direction
+    double* TMED;  // [S]    medium scatter distance
+    float* THR;    // [3][S] throughput
+    float* SUM;    // [3][S] radiance sum of the pixel
+    float* TIME;   // [S]
+    float* T;      // [S]    hit distance (fp32)
+    uint32_t* SB;  // [S]    sample << 8 | bounce
+    uint32_t* HIT; // [S]    hit id, or RT_HIT_NONE / RT_HIT_GEN_*
+    uint8_t* ready;
+    uint8_t* shade;
+    uint8_t* gen;
+    int S;
+    __device__ __forceinline__ Pool(char* p, int slots) : S(slots)
+    {
+        O = reinterpret_cast<double*>(p);
+        D = O + 3 * S;
+        TMED = D + 3 * S;
+        THR = reinterpret_cast<float*>(TMED + S);
+        SUM = THR + 3 * S;
+        TIME = SUM + 3 * S;
+        T = TIME + S;
+        SB = reinterpret_cast<uint32_t*>(T + S);
+        HIT = SB + S;
+        ready = reinterpret_cast<uint8_t*>(HIT + S);
+        shade = ready + S;
+        gen = shade + S;
+    }
+    __device__ __forceinline__ d3 LoadO(int s) const { return make_d3(O[s], O[S + s], O[2 * S + s]); }
+    __device__ __forceinline__ d3 LoadD(int s) const { return make_d3(D[s], D[S + s], D[2 * S + s]); }
+    __device__ __forceinline__ void StoreO(int s, const d3& v) const
+    {
+        O[s] = v.x;
+        O[S + s] = v.y;
+        O[2 * S + s] = v.z;
+    }
+    __device__ __forceinline__ void StoreD(int s, const d3& v) const
+    {
+        D[s] = v.x;
+        D[S + s] = v.y;
+        D[2 * S + s] = v.z;
+    }
+};
+__host__ __device__ constexpr int PoolBytes(int slots) { return slots * (7 * 8 + 10 * 4 + 3) + 16 - (slots * 3) % 16; }
+
+template <int FEAT, bool SMEM, bool STATS>
+__global__ void __launch_bounds__(512, 1) RenderWave(const DevScene scene, const DevCamera cam, const RenderArgs args)
+{
+    extern __shared__ __align__(16) char smem[];
+    const uint32_t smemBase = SmemAddr(smem);
+    uint32_t cursor = blockDim.x * 4u * (uint32_t)args.stackLevels;
+    const SceneView<SMEM> sv = SetupScene<SMEM>(scene, args, smem, smemBase, cursor);
+
+    Stack stack;
+    stack.base = smemBase + threadIdx.x * 4u;
+    stack.stride = blockDim.x * 4u;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu, ltMask = (1u << lane) - 1u;
+    const int S = args.waveSlots, tileH = S / 8;
+    const Pool pool(smem + ((cursor + 15u) & ~15u) + (uint32_t)warp * (uint32_t)PoolBytes(S), S);
+    const int nTiles = args.tilesX * args.tilesY;
+    const f3 background = make_f3(cam.background[0], cam.background[1], cam.background[2]);
+    const int idleExit = args.waveIdleExit, leafBatch = args.waveLeafBatch, refillMin = args.waveRefillMin;
+    unsigned long long nRays = 0, nPaths = 0, nNode = 0, nPrim = 0;
+
+    while (true) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(args.tileCounter, 1u);
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= nTiles) break;
+        const int tx = tile % args.tilesX, ty = tile / args.tilesX;
+        const int px0 = tx * 8, py0 = ty * tileH;
+
+        int nReady = 0, nShade = 0, nGen = 0;
+        for (int s = lane; s < S; s += 32) {
+            const bool valid = px0 + (s & 7) < cam.width && py0 + (s >> 3) < cam.height && args.sampleBegin < args.sampleEnd;
+            pool.SUM[s] = pool.SUM[S + s] = pool.SUM[2 * S + s] = 0.0f;
+            pool.SB[s] = (uint32_t)args.sampleBegin << 8;
+            pool.HIT[s] = RT_HIT_GEN_FIRST;
+            const unsigned m = __ballot_sync(FULL, valid);
+            if (valid) pool.gen[nGen + __popc(m & ltMask)] = (uint8_t)s;
+            nGen += __popc(m);
+        }
+        int nLive = nGen;
+
+        // EXTEND state of this lane (kept in registers across the other phases).
+        // An idle lane has tv.ref == RT_TRAV_DONE and mySlot < 0.
+        int mySlot = -1;
+        uint32_t myPixel = 0, mySB = 0;
+        Ray ray;
+        ray.o = make_d3(0.0, 0.0, 0.0);
+        ray.d = make_d3(1.0, 1.0, 1.0);
+        ray.time = 0.0f;
+        RaySlab slab = MakeSlab(ray);
+        double a = 3.0;
+        Trav tv;
+        tv.Begin(RT_TRAV_DONE);
+        tv.tMedium = 0.0;
+        unsigned idleMask = FULL;
+
+        while (nLive > 0) {
+            // ------------------------------------------------------------ EXTEND
+            while (true) {
+                const int nIdle = __popc(idleMask);
+                if (nReady > 0 && (nIdle >= refillMin || nIdle == 32)) {
+                    __syncwarp();
+                    const int take = min(nIdle, nReady);
+                    const int rank = __popc(idleMask & ltMask);
+                    if (mySlot < 0 && rank < take) {
+                        const int s = pool.ready[nReady - 1 - rank];
+                        mySlot = s;
+                        ray.o = pool.LoadO(s);
+                        ray.d = pool.LoadD(s);
+                        ray.time = pool.TIME[s];
+                        mySB = pool.SB[s];
+                        myPixel = (uint32_t)((py0 + (s >> 3)) * cam.width + px0 + (s & 7));
+                        slab = MakeSlab(ray);
+                        a = fma(ray.d.x, ray.d.x, fma(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
+                        tv.Begin(sv.root_ref);
+                    }
+                    nReady -= take;
+                    idleMask = __ballot_sync(FULL, mySlot < 0);
+                }
+                if (idleMask == FULL) break;
+                if (nReady == 0 && nShade + nGen > 0 && __popc(idleMask) >= idleExit) break;
+
+                // box steps, until `leafBatch` lanes wait at a leaf (or are done) or none is left
+                const unsigned flying = ~idleMask;
+                uint32_t nodeTests = 0, primTests = 0;
+                while (true) {
+                    const bool atBox = (tv.ref & RT_REF_LEAF) == 0u;
+                    const unsigned boxMask = __ballot_sync(FULL, atBox);
+                    if (boxMask == 0u || __popc(flying & ~boxMask) >= leafBatch) break;
+                    if (atBox) TraceBox<SMEM>(sv, slab, 0.001f, stack, tv, nodeTests);
+                }
+                // the leaves that piled up, together
+                if ((tv.ref & RT_REF_LEAF) != 0u && tv.ref != RT_TRAV_DONE)
+                    TraceLeaf<FEAT, SMEM>(sv, ray, a, 0.001f, stack, tv, args.seed, myPixel, mySB >> 8, (mySB & 0xffu) + 1u,
+                                          primTests);
+                if (STATS) {
+                    nNode += nodeTests;
+                    nPrim += primTests;
+                }
+                // retire finished walks: misses to `gen`, hits to `shade`
+                const bool fin = mySlot >= 0 && tv.ref == RT_TRAV_DONE;
+                const unsigned finMask = __ballot_sync(FULL, fin);
+                if (finMask != 0u) {
+                    const bool miss = fin && tv.hit == RT_HIT_NONE;
+                    const unsigned missMask = __ballot_sync(FULL, miss), hitMask = finMask & ~missMask;
+                    if (fin) {
+                        ++nRays;
+                        pool.HIT[mySlot] = tv.hit;
+                        pool.T[mySlot] = tv.t;
+                        if (FEAT & RT_FEAT_MEDIUM) pool.TMED[mySlot] = tv.tMedium;
+                        if (miss)
+                            pool.gen[nGen + __popc(missMask & ltMask)] = (uint8_t)mySlot;
+                        else
+                            pool.shade[nShade + __popc(hitMask & ltMask)] = (uint8_t)mySlot;
+                        mySlot = -1;
+                    }
+                    nGen += __popc(missMask);
+                    nShade += __popc(hitMask);
+                    idleMask |= finMask;
+                }
+            }
+
+            // ------------------------------------------------------------- SHADE
+            // full chunks of 32; a partial chunk only when nothing else can make progress
+            const bool starving = nShade < 32 && nGen < 32;
+            while (nShade >= 32 || (starving && nShade > 0)) {
+                __syncwarp();
+                const int n = min(nShade, 32);
+                const bool on = lane < n;
+                bool toReady = false, toGen = false;
+                int s = 0;
+                if (on) {
+                    s = pool.shade[nShade - n + lane];
+                    Ray r;
+                    r.o = pool.LoadO(s);
+                    r.d = pool.LoadD(s);
+                    r.time = pool.TIME[s];
+                    const uint32_t sb = pool.SB[s], hit = pool.HIT[s];
+                    const uint32_t sample = sb >> 8, bounce = sb & 0xffu;
+                    const uint32_t pixel = (uint32_t)((py0 + (s >> 3)) * cam.width + px0 + (s & 7));
+                    const double ra = fma(r.d.x, r.d.x, fma(r.d.y, r.d.y, r.d.z * r.d.z));
+                    Hit h;
+                    FinalizeHit<FEAT, SMEM>(sv, r, ra, hit, pool.T[s], (FEAT & RT_FEAT_MEDIUM) ? pool.TMED[s] : 0.0, h);
+                    if (STATS && args.debugOut && (int)pixel == args.debugPixel && (int)sample == args.debugSample) {
+                        float* o = args.debugOut + bounce * 8;
+                        o[0] = __uint_as_float(hit);
+                        o[1] = pool.T[s];
+                        o[2] = __int_as_float(h.material);
+                        o[3] = h.front ? 1.0f : 0.0f;
+                        o[4] = (float)h.p.x;
+                        o[5] = (float)h.p.y;
+                        o[6] = (float)h.p.z;
+                        o[7] = 1.0f;
+                    }
+                    const uint32_t type = RT_HIT_TYPE(hit);
+                    const bool sphereLike = type == RT_LEAF_SPHERE || type == RT_LEAF_MOVING;
+                    const StreamKey rng = MakeKey(args.seed, pixel, sample, bounce + 1u);
+                    f3 atten, emitted;
+                    d3 dir;
+                    const bool scattered = Scatter<FEAT, SMEM>(sv, h, r.d, ra, sphereLike, rng, atten, dir, emitted);
+                    const f3 thr = make_f3(pool.THR[s], pool.THR[S + s], pool.THR[2 * S + s]);
+                    if (!scattered) { // kernel.cu:82-83 (emission is black unless the path ends on a light)
+                        pool.SUM[s] += thr.x * emitted.x;
+                        pool.SUM[S + s] += thr.y * emitted.y;
+                        pool.SUM[2 * S + s] += thr.z * emitted.z;
+                    }
+                    if (scattered && (int)bounce + 1 < cam.max_depth) { // kernel.cu:93-94, :71
+                        pool.THR[s] = thr.x * atten.x;
+                        pool.THR[S + s] = thr.y * atten.y;
+                        pool.THR[2 * S + s] = thr.z * atten.z;
+                        pool.StoreO(s, h.p);
+                        pool.StoreD(s, dir);
+                        pool.SB[s] = sb + 1u;
+                        toReady = true;
+                    } else {
+                        pool.HIT[s] = RT_HIT_GEN_ENDED;
+                        toGen = true;
+                    }
+                }
+                nShade -= n;
+                const unsigned rm = __ballot_sync(FULL, toReady), gm = __ballot_sync(FULL, toGen);
+                if (toReady) pool.ready[nReady + __popc(rm & ltMask)] = (uint8_t)s;
+                if (toGen) pool.gen[nGen + __popc(gm & ltMask)] = (uint8_t)s;
+                nReady += __popc(rm);
+                nGen += __popc(gm);
+            }
+
+            // --------------------------------------------------------------- GEN
+            while (nGen >= 32 || (starving && nGen > 0)) {
+                __syncwarp();
+                const int n = min(nGen, 32);
+                const bool on = lane < n;
+                bool toReady = false, finished = false;
+                int s = 0;
+                if (on) {
+                    s = pool.gen[nGen - n + lane];
+                    const uint32_t hit = pool.HIT[s];
+                    uint32_t sample = pool.SB[s] >> 8;
+                    if (hit == RT_HIT_NONE) { // kernel.cu:74-79
+                        pool.SUM[s] += pool.THR[s] * background.x;
+                        pool.SUM[S + s] += pool.THR[S + s] * background.y;
+                        pool.SUM[2 * S + s] += pool.THR[2 * S + s] * background.z;
+                    }
+                    if (hit != RT_HIT_GEN_FIRST) ++sample;
+                    if ((int)sample >= args.sampleEnd) {
+                        finished = true;
+                    } else {
+                        const int i = px0 + (s & 7), j = py0 + (s >> 3);
+                        const StreamKey rng = MakeKey(args.seed, (uint32_t)(j * cam.width + i), sample, 0u);
+                        const Ray r = CameraRay(cam, i, j, rng);
+                        pool.StoreO(s, r.o);
+                        pool.StoreD(s, r.d);
+                        pool.TIME[s] = r.time;
+                        pool.THR[s] = pool.THR[S + s] = pool.THR[2 * S + s] = 1.0f;
+                        pool.SB[s] = sample << 8;
+                        toReady = true;
+                        if (STATS) ++nPaths;
+                    }
+                }
+                nGen -= n;
+                const unsigned rm = __ballot_sync(FULL, toReady), fm = __ballot_sync(FULL, finished);
+                if (toReady) pool.ready[nReady + __popc(rm & ltMask)] = (uint8_t)s;
+                nReady += __popc(rm);
+                nLive -= __popc(fm);
+            }
+        }
+
+        __syncwarp();
+        for (int s = lane; s < S; s += 32) {
+            const int i = px0 + (s & 7), j = py0 + (s >> 3);
+            if (i < cam.width && j < cam.height) {
+                float* px = args.accum + ((size_t)j * cam.width + i) * 3u;
+                px[0] += pool.SUM[s];
+                px[1] += pool.SUM[S + s];
+                px[2] += pool.SUM[2 * S + s];
+            }
+        }
+        __syncwarp();
+    }
+
+    for (int off = 16; off > 0; off >>= 1) {
+        nRays += __shfl_down_sync(FULL, nRays, off);
+        if (STATS) {
+            nPaths += __shfl_down_sync(FULL, nPaths, off);
+            nNode += __shfl_down_sync(FULL, nNode, off);
+            nPrim += __shfl_down_sync(FULL, nPrim, off);
         }
     }
     if (lane == 0) {
@@ -296,8 +641,12 @@ __global__ void FmaPeakKernel(float* out, int iters)
 
 using KernelFn = void (*)(const DevScene, const DevCamera, const RenderArgs);
 
-template <int FEAT> KernelFn PickKernel(bool smem, bool stats)
+template <int FEAT> KernelFn PickKernel(bool wave, bool smem, bool stats)
 {
+    if (wave) {
+        if (smem) return stats ? RenderWave<FEAT, true, true> : RenderWave<FEAT, true, false>;
+        return stats ? RenderWave<FEAT, false, true> : RenderWave<FEAT, false, false>;
+    }
     if (smem) return stats ? RenderMega<FEAT, true, true> : RenderMega<FEAT, true, false>;
     return stats ? RenderMega<FEAT, false, true> : RenderMega<FEAT, false, false>;
 }
@@ -307,18 +656,18 @@ constexpr int kFeatSpheres = 0;
 constexpr int kFeatMotion = RT_FEAT_MOVING | RT_FEAT_TEXTURE;
 constexpr int kFeatAll = RT_FEAT_MOVING | RT_FEAT_QUAD | RT_FEAT_MEDIUM | RT_FEAT_TEXTURE;
 
-KernelFn PickKernelForFeatures(int features, bool smem, bool stats, int* picked)
+KernelFn PickKernelForFeatures(int features, bool wave, bool smem, bool stats, int* picked)
 {
     if (features == 0) {
         *picked = kFeatSpheres;
-        return PickKernel<kFeatSpheres>(smem, stats);
+        return PickKernel<kFeatSpheres>(wave, smem, stats);
     }
     if ((features & ~kFeatMotion) == 0) {
         *picked = kFeatMotion;
-        return PickKernel<kFeatMotion>(smem, stats);
+        return PickKernel<kFeatMotion>(wave, smem, stats);
     }
     *picked = kFeatAll;
-    return PickKernel<kFeatAll>(smem, stats);
+    return PickKernel<kFeatAll>(wave, smem, stats);
 }
 
 template <class T> int UploadVec(const std::vector<T>& v, T** dev, uint64_t* bytes)
@@ -491,10 +840,11 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
         rt_set_error("rt_render: image too large");
         return RT_ERR_INVALID;
     }
-    if (p->variant == RT_VARIANT_WAVEFRONT) {
-        rt_set_error("rt_render: the wavefront variant is not built in this version");
-        return RT_ERR_UNSUPPORTED;
+    if (p->variant < RT_VARIANT_AUTO || p->variant > RT_VARIANT_WAVEFRONT) {
+        rt_set_error("rt_render: unknown variant %d", p->variant);
+        return RT_ERR_INVALID;
     }
+    const bool wave = p->variant == RT_VARIANT_WAVEFRONT;
     RT_CUDA(cudaSetDevice(h->device));
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
     const size_t nFloats = (size_t)cam->image_width * cam->image_height * 3;
@@ -526,8 +876,16 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     a.debugPixel = h->debugPixel;
     a.debugSample = h->debugSample;
     a.debugOut = h->debugPixel >= 0 ? h->debugOut : nullptr;
-    a.tilesX = (cam->image_width + kTileW - 1) / kTileW;
-    a.tilesY = (cam->image_height + kTileH - 1) / kTileH;
+    // tiles: 8x4 pixels per warp (megakernel: one pixel per lane) or 8x8 (wavefront: 64 path slots)
+    // tuning knobs of the wavefront variant (development): flags bits 12-15 slots/32,
+    // 16-20 idle-exit, 21-25 leaf batch, 26-30 refill minimum
+    int waveSlots = ((p->flags >> 12) & 0xf) * 32;
+    a.waveIdleExit = (p->flags >> 16) & 0x1f;
+    a.waveLeafBatch = (p->flags >> 21) & 0x1f;
+    a.waveRefillMin = (p->flags >> 26) & 0x1f;
+    if (a.waveIdleExit <= 0) a.waveIdleExit = 12;
+    if (a.waveLeafBatch <= 0) a.waveLeafBatch = 12;
+    if (a.waveRefillMin <= 0) a.waveRefillMin = 6;
     auto pad16 = [](size_t b) { return (uint32_t)((b + 15) / 16 * 16); };
     const rtpack::Packed& pk = *h->host;
     a.nodesBytes = pad16(std::max<size_t>(1, pk.nodes.size()) * sizeof(DevNode));
@@ -538,21 +896,45 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     a.mediaBytes = pad16(std::max<size_t>(1, pk.media.size()) * sizeof(DevMedium));
     a.materialsBytes = pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial));
 
-    int threads = p->block_threads > 0 ? p->block_threads : 512;
-    threads = std::max(32, std::min(1024, (threads / 32) * 32));
+    const int maxThreads = wave ? 512 : MegaMaxThreads(h->dev.features == 0 ? 0 : 1);
+    int threads = p->block_threads > 0 ? p->block_threads : maxThreads;
+    threads = std::max(32, std::min(maxThreads, (threads / 32) * 32));
     int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;
     const int stackLevels = std::max(2, std::min(kMaxStackLevels, h->host->max_depth + 2));
     a.stackLevels = stackLevels;
+    if (wave) {
+        threads = std::min(threads, 512); // __launch_bounds__(512, 1)
+        blocksPerSm = 1;
+    }
     const size_t stackBytes = (size_t)threads * 4 * stackLevels;
+    size_t poolBytes = 0;
+    if (wave) {
+        // largest pool (more slots = fuller SHADE/GEN chunks) that still leaves room for the scene
+        auto bytesFor = [&](int slots) { return (size_t)(threads / 32) * PoolBytes(slots) + 16; };
+        if (waveSlots < 64 || waveSlots > 128) {
+            waveSlots = 64;
+            for (int cand : {128, 96})
+                if (stackBytes + bytesFor(cand) + h->stagedBytes <= (size_t)h->maxSmemOptin) {
+                    waveSlots = cand;
+                    break;
+                }
+        }
+        poolBytes = bytesFor(waveSlots);
+    }
+    a.waveSlots = waveSlots;
+    const int tileH = wave ? waveSlots / 8 : kTileH;
+    a.tilesX = (cam->image_width + kTileW - 1) / kTileW;
+    a.tilesY = (cam->image_height + tileH - 1) / tileH;
     const bool wantStats = (p->flags & 0x100) != 0 || a.debugOut != nullptr;
-    const bool smem = !(p->flags & 0x200) && stackBytes + h->stagedBytes <= (size_t)h->maxSmemOptin / (size_t)blocksPerSm;
-    const size_t smemBytes = stackBytes + (smem ? h->stagedBytes : 0);
+    const bool smem = !(p->flags & 0x200) &&
+                      stackBytes + poolBytes + h->stagedBytes <= (size_t)h->maxSmemOptin / (size_t)blocksPerSm;
+    const size_t smemBytes = stackBytes + poolBytes + (smem ? h->stagedBytes : 0);
     if (smemBytes > (size_t)h->maxSmemOptin) {
         rt_set_error("rt_render: block of %d threads needs %zu B of shared memory (max %d)", threads, smemBytes,
                      h->maxSmemOptin);
         return RT_ERR_INVALID;
     }
-    KernelFn fn = PickKernelForFeatures(h->dev.features, smem, wantStats, &h->pickedFeatures);
+    KernelFn fn = PickKernelForFeatures(h->dev.features, wave, smem, wantStats, &h->pickedFeatures);
     RT_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     const int nTiles = a.tilesX * a.tilesY;
     const int warpsPerBlock = threads / 32;

@@ -510,48 +510,63 @@ struct Trav {
     }
 };
 
+RT_DEV void TravPop(const Stack& stack, Trav& tv) { tv.ref = tv.sp == 0 ? RT_TRAV_DONE : stack.Pop(--tv.sp); }
+
+// One internal node: both children boxes tested, nearer one entered first.
+template <bool SMEM>
+RT_DEV void TraceBox(const SceneView<SMEM>& sv, const RaySlab& slab, float tmin, const Stack& stack, Trav& tv, uint32_t& nodeTests)
+{
+    const uint32_t off = tv.ref * 32u;
+    const float4 lo0 = Ld4<SMEM>(sv.nodes, off);
+    const float4 hi0 = Ld4<SMEM>(sv.nodes, off + 16u);
+    const float4 lo1 = Ld4<SMEM>(sv.nodes, off + 32u);
+    const float4 hi1 = Ld4<SMEM>(sv.nodes, off + 48u);
+    nodeTests += 2;
+    const float e0 = SlabEntry(lo0, hi0, slab, tmin, tv.t);
+    const float e1 = SlabEntry(lo1, hi1, slab, tmin, tv.t);
+    const uint32_t r0 = (uint32_t)__float_as_int(lo0.w), r1 = (uint32_t)__float_as_int(lo1.w);
+    const bool h0 = e0 < 3.0e38f, h1 = e1 < 3.0e38f;
+    if (h0 && h1) {
+        const bool swap = e1 < e0;
+        stack.Push(tv.sp++, swap ? r0 : r1);
+        tv.ref = swap ? r1 : r0;
+    } else if (h0 || h1) {
+        tv.ref = h0 ? r0 : r1;
+    } else {
+        TravPop(stack, tv);
+    }
+}
+
+// One leaf: a typed run of primitives, or a medium.
+template <int FEAT, bool SMEM>
+RT_DEV void TraceLeaf(const SceneView<SMEM>& sv, const Ray& r, double a, float tmin, const Stack& stack, Trav& tv,
+                      uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
+{
+    const uint32_t ref = tv.ref;
+    if ((FEAT & RT_FEAT_MEDIUM) && RT_REF_TYPE(ref) == RT_LEAF_MEDIUM) {
+        const uint32_t m = RT_REF_FIRST(ref);
+        double tm;
+        if (HitMedium<FEAT, SMEM>(sv, m, r, a, tmin, tv.t, seed, pixel, sample, slot, primTests, tm)) {
+            tv.t = (float)tm;
+            tv.tMedium = tm;
+            tv.hit = RT_HIT_MAKE(RT_LEAF_MEDIUM, m);
+        }
+    } else {
+        const uint32_t h = HitRun<FEAT, SMEM>(sv, ref, r, a, (double)tmin, tv.t, primTests);
+        if (h != RT_HIT_NONE) tv.hit = h;
+    }
+    TravPop(stack, tv);
+}
+
 template <int FEAT, bool SMEM>
 RT_DEV void TraceStep(const SceneView<SMEM>& sv, const Ray& r, const RaySlab& slab, double a, float tmin, const Stack& stack,
                       Trav& tv, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& nodeTests,
                       uint32_t& primTests)
 {
-    const uint32_t ref = tv.ref;
-    if (!(ref & RT_REF_LEAF)) {
-        const uint32_t off = ref * 32u;
-        const float4 lo0 = Ld4<SMEM>(sv.nodes, off);
-        const float4 hi0 = Ld4<SMEM>(sv.nodes, off + 16u);
-        const float4 lo1 = Ld4<SMEM>(sv.nodes, off + 32u);
-        const float4 hi1 = Ld4<SMEM>(sv.nodes, off + 48u);
-        nodeTests += 2;
-        const float e0 = SlabEntry(lo0, hi0, slab, tmin, tv.t);
-        const float e1 = SlabEntry(lo1, hi1, slab, tmin, tv.t);
-        const uint32_t r0 = (uint32_t)__float_as_int(lo0.w), r1 = (uint32_t)__float_as_int(lo1.w);
-        const bool h0 = e0 < 3.0e38f, h1 = e1 < 3.0e38f;
-        if (h0 && h1) {
-            const bool swap = e1 < e0;
-            stack.Push(tv.sp++, swap ? r0 : r1);
-            tv.ref = swap ? r1 : r0;
-            return;
-        }
-        if (h0 || h1) {
-            tv.ref = h0 ? r0 : r1;
-            return;
-        }
-    } else {
-        if ((FEAT & RT_FEAT_MEDIUM) && RT_REF_TYPE(ref) == RT_LEAF_MEDIUM) {
-            const uint32_t m = RT_REF_FIRST(ref);
-            double tm;
-            if (HitMedium<FEAT, SMEM>(sv, m, r, a, tmin, tv.t, seed, pixel, sample, slot, primTests, tm)) {
-                tv.t = (float)tm;
-                tv.tMedium = tm;
-                tv.hit = RT_HIT_MAKE(RT_LEAF_MEDIUM, m);
-            }
-        } else {
-            const uint32_t h = HitRun<FEAT, SMEM>(sv, ref, r, a, (double)tmin, tv.t, primTests);
-            if (h != RT_HIT_NONE) tv.hit = h;
-        }
-    }
-    tv.ref = tv.sp == 0 ? RT_TRAV_DONE : stack.Pop(--tv.sp);
+    if (!(tv.ref & RT_REF_LEAF))
+        TraceBox<SMEM>(sv, slab, tmin, stack, tv, nodeTests);
+    else
+        TraceLeaf<FEAT, SMEM>(sv, r, a, tmin, stack, tv, seed, pixel, sample, slot, primTests);
 }
 
 // ----------------------------------------------------------------- textures
@@ -648,40 +663,49 @@ template <bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv, int tex, 
 }
 
 // ---------------------------------------------------------------- scatter
-struct DrawStream {
-    uint32_t seed, pixel, sample, slot, dim;
-    rt_u4 cur;
-    RT_DEV void Begin(uint32_t seed_, uint32_t pixel_, uint32_t sample_, uint32_t slot_)
-    {
-        seed = seed_;
-        pixel = pixel_;
-        sample = sample_;
-        slot = slot_;
-        dim = 0;
-    }
-    RT_DEV float Next()
-    {
-        const uint32_t lane = dim & 3u;
-        if (lane == 0) cur = rt_rng_block(seed, pixel, sample, slot, 0, dim >> 2);
-        ++dim;
-        return rt_bits_to_u01(rt_u4_lane(cur, lane));
-    }
+// The sequential draws of one (pixel, sample, slot) stream, domain 0 (rt_rng.h).
+// Draw number `dim` is lane dim&3 of block dim>>2; the two users below walk the
+// blocks explicitly, so no lane selects or per-draw bookkeeping are executed.
+struct StreamKey {
+    uint32_t seed, pixel, sample, slot;
+    RT_DEV rt_u4 Block(uint32_t block) const { return rt_rng_block(seed, pixel, sample, slot, 0, block); }
 };
-
-// Material.h:14-24.  The candidate is exact in FP64 (2x-1 of a 24-bit x); the
-// rejection test is decided in fp32 unless it is within rounding of the sphere.
-RT_DEV d3 RandomInUnitSphere(DrawStream& rng)
+RT_DEV StreamKey MakeKey(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot)
 {
-    while (true) {
-        const float x = rng.Next();
-        const float y = rng.Next();
-        const float z = rng.Next();
-        const float fx = 2.0f * x - 1.0f, fy = 2.0f * y - 1.0f, fz = 2.0f * z - 1.0f;
-        const float l2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
-        if (l2 >= 1.00001f) continue;
-        const d3 p = make_d3(fma(2.0, (double)x, -1.0), fma(2.0, (double)y, -1.0), fma(2.0, (double)z, -1.0));
-        if (l2 > 0.99999f && dot(p, p) >= 1.0) continue;
-        return p;
+    StreamKey k;
+    k.seed = seed;
+    k.pixel = pixel;
+    k.sample = sample;
+    k.slot = slot;
+    return k;
+}
+
+// One candidate of Material.h:14-24 from three 32-bit draws.  The candidate is
+// exact in FP64 (2x-1 of a 24-bit x); the rejection test is decided in fp32
+// unless it is within rounding of the sphere.
+RT_DEV bool BallCandidate(uint32_t bx, uint32_t by, uint32_t bz, d3& p)
+{
+    const float x = rt_bits_to_u01(bx), y = rt_bits_to_u01(by), z = rt_bits_to_u01(bz);
+    const float fx = 2.0f * x - 1.0f, fy = 2.0f * y - 1.0f, fz = 2.0f * z - 1.0f;
+    const float l2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+    if (l2 >= 1.00001f) return false;
+    p = make_d3(fma(2.0, (double)x, -1.0), fma(2.0, (double)y, -1.0), fma(2.0, (double)z, -1.0));
+    return !(l2 > 0.99999f && dot(p, p) >= 1.0);
+}
+
+// Material.h:14-24, drawing from the start of the slot's stream: candidate k
+// uses draws 3k..3k+2, i.e. four candidates per three blocks.
+RT_DEV d3 RandomInUnitSphere(const StreamKey& key)
+{
+    d3 p;
+    for (uint32_t blk = 0;; blk += 3) {
+        const rt_u4 b0 = key.Block(blk);
+        if (BallCandidate(b0.x, b0.y, b0.z, p)) return p;
+        const rt_u4 b1 = key.Block(blk + 1u);
+        if (BallCandidate(b0.w, b1.x, b1.y, p)) return p;
+        const rt_u4 b2 = key.Block(blk + 2u);
+        if (BallCandidate(b1.z, b1.w, b2.x, p)) return p;
+        if (BallCandidate(b2.y, b2.z, b2.w, p)) return p;
     }
 }
 
@@ -692,7 +716,7 @@ RT_DEV d3 Reflect(d3 v, d3 n) { return v - (2.0 * dot(v, n)) * n; } // Vec3.h:12
 // `atten` the attenuation.  `emitted` is Material::Emitted (black unless light).
 // `a` = |dirIn|^2.
 template <int FEAT, bool SMEM>
-RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, const d3& dirIn, double a, bool sphereLike, DrawStream& rng,
+RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, const d3& dirIn, double a, bool sphereLike, const StreamKey& rng,
                     f3& atten, d3& dir, f3& emitted)
 {
     const float4 m0 = Ld4<SMEM>(sv.materials, (uint32_t)h.material * 32u);
@@ -729,7 +753,7 @@ RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, const d3& dirIn, do
             r0 = r0 * r0;
             const float k = 1.0f - cosF;
             const float k2 = k * k;
-            reflect = r0 + (1.0f - r0) * (k2 * k2 * k) > rng.Next();
+            reflect = r0 + (1.0f - r0) * (k2 * k2 * k) > rt_bits_to_u01(rng.Block(0).x);
         }
         if (reflect) {
             dir = Reflect(ud, h.n);
@@ -753,25 +777,41 @@ RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, const d3& dirIn, do
 // ------------------------------------------------------------------- camera
 // kernel.cu:140-142 + Camera.h:10-19,76-85: jitter (int + float sum in fp32),
 // lens disk by rejection (always drawn), shutter time (always drawn).
-RT_DEV Ray CameraRay(const DevCamera& cam, int i, int j, DrawStream& rng)
+RT_DEV Ray CameraRay(const DevCamera& cam, int i, int j, const StreamKey& rng)
 {
-    const float fu = (float)i + rng.Next();
-    const float fv = (float)j + rng.Next();
+    // draws 0,1: jitter; then pairs (2,3),(4,5),.. until one lies in the disk; then the time
+    rt_u4 b = rng.Block(0);
+    const float fu = (float)i + rt_bits_to_u01(b.x);
+    const float fv = (float)j + rt_bits_to_u01(b.y);
     const double s = (double)fu / (double)cam.width;
     const double t = (double)fv / (double)cam.height;
-    float px, py;
-    do {
-        const float x = rng.Next();
-        const float y = rng.Next();
-        px = 2.0f * x - 1.0f;
-        py = 2.0f * y - 1.0f;
-    } while (px * px + py * py >= 1.0f);
+    float px = 2.0f * rt_bits_to_u01(b.z) - 1.0f, py = 2.0f * rt_bits_to_u01(b.w) - 1.0f;
+    uint32_t timeBits;
+    if (px * px + py * py < 1.0f) {
+        timeBits = rng.Block(1).x;
+    } else {
+        for (uint32_t blk = 1;; ++blk) {
+            b = rng.Block(blk);
+            px = 2.0f * rt_bits_to_u01(b.x) - 1.0f;
+            py = 2.0f * rt_bits_to_u01(b.y) - 1.0f;
+            if (px * px + py * py < 1.0f) {
+                timeBits = b.z;
+                break;
+            }
+            px = 2.0f * rt_bits_to_u01(b.z) - 1.0f;
+            py = 2.0f * rt_bits_to_u01(b.w) - 1.0f;
+            if (px * px + py * py < 1.0f) {
+                timeBits = rng.Block(blk + 1u).x;
+                break;
+            }
+        }
+    }
     const double rdx = cam.lens_radius * (double)px, rdy = cam.lens_radius * (double)py;
     const double offx = cam.u[0] * rdx + cam.v[0] * rdy;
     const double offy = cam.u[1] * rdx + cam.v[1] * rdy;
     const double offz = cam.u[2] * rdx + cam.v[2] * rdy;
     Ray r;
-    r.time = cam.time0 + rng.Next() * (cam.time1 - cam.time0);
+    r.time = cam.time0 + rt_bits_to_u01(timeBits) * (cam.time1 - cam.time0);
     r.o.x = cam.origin[0] + offx;
     r.o.y = cam.origin[1] + offy;
     r.o.z = cam.origin[2] + offz;

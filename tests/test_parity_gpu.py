@@ -91,6 +91,28 @@ def test_shared_memory_and_global_paths_are_bit_identical():
     assert np.array_equal(a, b) and sa.rays == sb.rays
 
 
+@pytest.mark.parametrize("sid,W,H,spp", [(10, 200, 113, 6), (0, 96, 54, 4), (7, 64, 64, 6), (8, 64, 64, 6), (9, 96, 54, 3)])
+def test_wavefront_variant_renders_the_same_image_as_the_megakernel(earth, sid, W, H, spp):
+    """Same per-pixel sample order and the same device functions: the on-chip wavefront
+    kernel must reproduce the megakernel's sums (and so inherits its parity with the oracle)."""
+    sc = scene_for(sid, earth)
+    cam = sc.camera(W, H, spp, 50)
+    a, sa, _ = gpu_render(sc, cam, variant=A.RT_VARIANT_MEGAKERNEL)
+    b, sb, _ = gpu_render(sc, cam, variant=A.RT_VARIANT_WAVEFRONT)
+    assert sa.rays == sb.rays
+    assert np.allclose(a, b, rtol=1e-6, atol=1e-7)
+    assert (a == b).mean() > 0.999
+
+
+def test_wavefront_variant_parity_with_the_oracle(oracle):
+    sc = BuiltinScene(10)
+    cam = sc.camera(240, 135, 4, 50)
+    want, ost = oracle_render(oracle, sc, cam, 0, 4)
+    got, st, _ = gpu_render(sc, cam, variant=A.RT_VARIANT_WAVEFRONT, block_threads=128)
+    assert match_fraction(got, want, 4) >= MIN_MATCH
+    assert abs(int(st.rays) - int(ost.rays)) <= 2e-3 * ost.rays
+
+
 def test_deterministic_and_block_shape_independent():
     sc = BuiltinScene(0)
     cam = sc.camera(100, 57, 3, 50)  # not a multiple of the 8x4 tile

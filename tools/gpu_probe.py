@@ -153,6 +153,30 @@ if "sweep" in what:
     with open(os.path.join(OUT, "probe_sweep.json"), "w") as f:
         json.dump(rows, f, indent=1)
 
+if "wave" in what:
+    rows = []
+    sc = BuiltinScene(10)
+    cam = sc.camera(3840, 2160, 16, 50)
+    r = Renderer(sc.desc)
+    ms, st = timed(r, cam, reps=2)
+    print({"variant": "mega", "ms": ms, "grays_s": st.rays / ms / 1e6}, flush=True)
+    for threads, slots in ((512, 64), (512, 96), (448, 96), (384, 96), (384, 128), (320, 128)):
+        for idle in (8, 16, 24):
+            for leaf in (8, 16, 24):
+                for refill in (1, 8, 16):
+                    fl = ((slots // 32) << 12) | (idle << 16) | (leaf << 21) | (refill << 26)
+                    try:
+                        ms, st = timed(r, cam, reps=2, variant=2, block_threads=threads, flags=fl)
+                    except Exception as e:  # noqa: BLE001
+                        print("skip", threads, slots, idle, leaf, refill, str(e)[:80])
+                        break
+                    rows.append({"threads": threads, "slots": slots, "idle_exit": idle, "leaf_batch": leaf, "refill_min": refill,
+                                 "ms": ms, "grays_s": st.rays / ms / 1e6})
+                    print(rows[-1], flush=True)
+    r.close()
+    with open(os.path.join(OUT, "probe_wave.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+
 if "diverge" in what:
     # per-sample comparison: find (pixel, sample) paths whose radiance differs, dump both paths
     out = {}
