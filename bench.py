@@ -329,10 +329,17 @@ def run_b200_arm():
         A = sys.modules["raytracinginoneweekendincuda_b200._abi"]
         lib = r.lib
 
+        trace = os.environ.get("RT_BENCH_TRACE")
+
         def step_e2e():
+            t = [time.perf_counter()]
             flush.zero_()
             rr = Renderer(sc.desc, device=local)  # deep copy + bake + BVH + H2D of every table
+            t.append(time.perf_counter())
             rr.render(cam, s0, s1, clear=True, **kw)
+            if trace:
+                torch.cuda.synchronize()
+            t.append(time.perf_counter())
             if world > 1:
                 reduce_accumulators(accum, dst=0)
             if rank == 0:
@@ -342,7 +349,12 @@ def run_b200_arm():
                 assert rc == 0, lib.rt_last_error()
             else:
                 rr.sync()
+            t.append(time.perf_counter())
             rr.close()
+            t.append(time.perf_counter())
+            if trace:
+                print("e2e step: upload %.1f render %.1f reduce+readback %.1f free %.1f ms" %
+                      tuple(1e3 * (b - a) for a, b in zip(t, t[1:])), file=sys.stderr, flush=True)
 
         step_e2e()
         barrier()

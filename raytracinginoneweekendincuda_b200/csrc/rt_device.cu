@@ -25,6 +25,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -670,18 +671,66 @@ KernelFn PickKernelForFeatures(int features, bool wave, bool smem, bool stats, i
     return PickKernel<kFeatAll>(wave, smem, stats);
 }
 
-template <class T> int UploadVec(const std::vector<T>& v, T** dev, uint64_t* bytes)
+// Frame-sized device buffers (accumulator, readback staging) are recycled across
+// handles: cudaMalloc/cudaFree of ~100 MB blocks was measured at up to 0.5 s per
+// upload/free cycle, which is what an application rendering frame after frame does.
+struct BigBlock {
+    int device;
+    size_t bytes;
+    void* ptr;
+};
+std::mutex gBigMutex;
+std::vector<BigBlock> gBigCache;
+constexpr size_t kBigCacheEntries = 8;
+
+cudaError_t BigMalloc(int device, void** out, size_t bytes)
 {
-    *dev = nullptr;
-    // always allocate at least one record so staging code can read 16 bytes
-    const size_t n = v.empty() ? 1 : v.size();
-    const size_t sz = ((n * sizeof(T) + 15) / 16) * 16;
-    RT_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), sz));
-    RT_CUDA(cudaMemset(*dev, 0, sz));
-    if (!v.empty()) RT_CUDA(cudaMemcpy(*dev, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *bytes += sz;
-    return RT_OK;
+    {
+        std::lock_guard<std::mutex> lock(gBigMutex);
+        for (size_t k = 0; k < gBigCache.size(); ++k)
+            if (gBigCache[k].device == device && gBigCache[k].bytes == bytes) {
+                *out = gBigCache[k].ptr;
+                gBigCache.erase(gBigCache.begin() + (long)k);
+                return cudaSuccess;
+            }
+    }
+    return cudaMalloc(out, bytes);
 }
+
+void BigFree(int device, void* ptr, size_t bytes)
+{
+    if (!ptr) return;
+    {
+        std::lock_guard<std::mutex> lock(gBigMutex);
+        if (gBigCache.size() < kBigCacheEntries) {
+            gBigCache.push_back(BigBlock{device, bytes, ptr});
+            return;
+        }
+    }
+    cudaFree(ptr);
+}
+
+// Host image of the device arena: every table of the scene back to back, 256-byte
+// aligned, so that one allocation and ONE host-to-device copy upload the scene
+// (and one ncclBroadcast would replicate it).
+struct ArenaBuilder {
+    std::vector<char> bytes;
+    template <class T> size_t Add(const std::vector<T>& v)
+    {
+        // at least one zeroed record so that staging code can always read 16 bytes
+        const size_t n = v.empty() ? 1 : v.size();
+        const size_t at = (bytes.size() + 255) / 256 * 256;
+        bytes.resize(at + (n * sizeof(T) + 15) / 16 * 16, 0);
+        if (!v.empty()) std::memcpy(bytes.data() + at, v.data(), v.size() * sizeof(T));
+        return at;
+    }
+    size_t Reserve(size_t n)
+    {
+        const size_t at = (bytes.size() + 255) / 256 * 256;
+        bytes.resize(at + (n + 15) / 16 * 16, 0);
+        return at;
+    }
+};
 
 } // namespace
 
@@ -689,8 +738,8 @@ struct rt_scene_s {
     int device = 0;
     DevScene dev{};
     rtpack::Packed* host = nullptr; // kept for sizes / info
-    std::vector<void*> allocations;
-    std::vector<DevImage> images;
+    char* arena = nullptr; // one device block: scene tables, images, counters, debug records
+    size_t arenaBytes = 0;
     uint64_t deviceBytes = 0;
     bool fitsSmem = false;
     uint32_t stagedBytes = 0;
@@ -749,56 +798,62 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
     rt_scene_s* h = new rt_scene_s();
     h->device = o.device;
     h->host = packed;
-    cudaDeviceProp prop;
-    RT_CUDA(cudaGetDeviceProperties(&prop, o.device));
-    h->smCount = prop.multiProcessorCount;
-    h->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
+    // two attributes, not cudaGetDeviceProperties: the full query costs tens of ms per call
+    RT_CUDA(cudaDeviceGetAttribute(&h->smCount, cudaDevAttrMultiProcessorCount, o.device));
+    RT_CUDA(cudaDeviceGetAttribute(&h->maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
 
-#define RT_UP(field, vec, T)                                                         \
-    do {                                                                             \
-        T* p_ = nullptr;                                                             \
-        int rc_ = UploadVec<T>(vec, &p_, &h->deviceBytes);                           \
-        if (rc_ != RT_OK) {                                                          \
-            rt_scene_free(h);                                                        \
-            return rc_;                                                              \
-        }                                                                            \
-        h->allocations.push_back(p_);                                                \
-        h->dev.field = p_;                                                           \
-    } while (0)
-    RT_UP(nodes, packed->nodes, DevNode);
-    RT_UP(spheres, packed->spheres, DevSphere);
-    RT_UP(sphere_material, packed->sphere_material, int32_t);
-    RT_UP(moving, packed->moving, DevMovingSphere);
-    RT_UP(quads, packed->quads, DevQuad);
-    RT_UP(media, packed->media, DevMedium);
-    RT_UP(materials, packed->materials, DevMaterial);
-    RT_UP(textures, packed->textures, DevTexture);
-    RT_UP(perlins, packed->perlins, DevPerlin);
-#undef RT_UP
-    for (size_t k = 0; k < packed->image_bytes.size(); ++k) {
+    ArenaBuilder ab;
+    const size_t oNodes = ab.Add(packed->nodes), oSpheres = ab.Add(packed->spheres);
+    const size_t oSphereMat = ab.Add(packed->sphere_material), oMoving = ab.Add(packed->moving);
+    const size_t oQuads = ab.Add(packed->quads), oMedia = ab.Add(packed->media), oMaterials = ab.Add(packed->materials);
+    const size_t oTextures = ab.Add(packed->textures), oPerlins = ab.Add(packed->perlins);
+    std::vector<size_t> oImage(packed->image_bytes.size(), 0);
+    for (size_t k = 0; k < packed->image_bytes.size(); ++k)
+        if (!packed->image_bytes[k].empty()) oImage[k] = ab.Add(packed->image_bytes[k]);
+    const size_t oImages = ab.Reserve(std::max<size_t>(1, packed->image_bytes.size()) * sizeof(DevImage));
+    const size_t oStats = ab.Reserve(4 * sizeof(unsigned long long)), oTile = ab.Reserve(sizeof(unsigned int));
+    const size_t oDebug = ab.Reserve(256 * 8 * sizeof(float));
+    h->arenaBytes = (ab.bytes.size() + 255) / 256 * 256;
+    ab.bytes.resize(h->arenaBytes, 0);
+    {
+        void* p = nullptr;
+        const cudaError_t e = BigMalloc(h->device, &p, h->arenaBytes);
+        if (e != cudaSuccess) {
+            rt_set_error("rt_scene_upload: cudaMalloc of %zu bytes failed: %s", h->arenaBytes, cudaGetErrorString(e));
+            rt_scene_free(h);
+            return RT_ERR_CUDA;
+        }
+        h->arena = static_cast<char*>(p);
+    }
+    for (size_t k = 0; k < packed->image_bytes.size(); ++k) { // image table: device addresses inside the arena
         DevImage im{};
         im.width = packed->image_w[k];
         im.height = packed->image_h[k];
-        if (!packed->image_bytes[k].empty()) {
-            uint8_t* p = nullptr;
-            RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), packed->image_bytes[k].size()));
-            RT_CUDA(cudaMemcpy(p, packed->image_bytes[k].data(), packed->image_bytes[k].size(), cudaMemcpyHostToDevice));
-            h->allocations.push_back(p);
-            h->deviceBytes += packed->image_bytes[k].size();
-            im.rgb = p;
-        }
-        h->images.push_back(im);
+        im.rgb = packed->image_bytes[k].empty() ? nullptr : reinterpret_cast<const uint8_t*>(h->arena + oImage[k]);
+        std::memcpy(ab.bytes.data() + oImages + k * sizeof(DevImage), &im, sizeof im);
     }
     {
-        DevImage* p = nullptr;
-        int rc = UploadVec<DevImage>(h->images, &p, &h->deviceBytes);
-        if (rc != RT_OK) {
+        const cudaError_t e = cudaMemcpy(h->arena, ab.bytes.data(), h->arenaBytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            rt_set_error("rt_scene_upload: host-to-device copy failed: %s", cudaGetErrorString(e));
             rt_scene_free(h);
-            return rc;
+            return RT_ERR_CUDA;
         }
-        h->allocations.push_back(p);
-        h->dev.images = p;
     }
+    h->deviceBytes = h->arenaBytes;
+    h->dev.nodes = reinterpret_cast<const DevNode*>(h->arena + oNodes);
+    h->dev.spheres = reinterpret_cast<const DevSphere*>(h->arena + oSpheres);
+    h->dev.sphere_material = reinterpret_cast<const int32_t*>(h->arena + oSphereMat);
+    h->dev.moving = reinterpret_cast<const DevMovingSphere*>(h->arena + oMoving);
+    h->dev.quads = reinterpret_cast<const DevQuad*>(h->arena + oQuads);
+    h->dev.media = reinterpret_cast<const DevMedium*>(h->arena + oMedia);
+    h->dev.materials = reinterpret_cast<const DevMaterial*>(h->arena + oMaterials);
+    h->dev.textures = reinterpret_cast<const DevTexture*>(h->arena + oTextures);
+    h->dev.perlins = reinterpret_cast<const DevPerlin*>(h->arena + oPerlins);
+    h->dev.images = reinterpret_cast<const DevImage*>(h->arena + oImages);
+    h->stats = reinterpret_cast<unsigned long long*>(h->arena + oStats);
+    h->tileCounter = reinterpret_cast<unsigned int*>(h->arena + oTile);
+    h->debugOut = reinterpret_cast<float*>(h->arena + oDebug);
     h->dev.root_ref = packed->root_ref;
     h->dev.n_nodes = (int)packed->nodes.size();
     h->dev.n_spheres = (int)packed->spheres.size();
@@ -818,9 +873,6 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
                      pad16(std::max<size_t>(1, packed->media.size()) * sizeof(DevMedium)) +
                      pad16(std::max<size_t>(1, packed->materials.size()) * sizeof(DevMaterial));
 
-    RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->stats), 4 * sizeof(unsigned long long)));
-    RT_CUDA(cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long)));
-    RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->tileCounter), sizeof(unsigned int)));
     *out = h;
     return RT_OK;
 }
@@ -851,9 +903,10 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     float* accum = p->accum;
     if (!accum) {
         if (h->accumFloats != nFloats) {
-            if (h->accum) RT_CUDA(cudaFree(h->accum));
+            BigFree(h->device, h->accum, h->accumFloats * sizeof(float));
             h->accum = nullptr;
-            RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->accum), nFloats * sizeof(float)));
+            h->accumFloats = 0;
+            RT_CUDA(BigMalloc(h->device, reinterpret_cast<void**>(&h->accum), nFloats * sizeof(float)));
             h->accumFloats = nFloats;
             RT_CUDA(cudaMemsetAsync(h->accum, 0, nFloats * sizeof(float), stream));
         }
@@ -992,17 +1045,17 @@ int rt_readback(rt_scene_handle h, const float* accum, float* linear_rgb, uint8_
     cudaStream_t stream = h->lastStream;
     if (linear_rgb || srgb8) {
         if (linear_rgb && h->linearStageFloats < nFloats) {
-            if (h->linearStage) RT_CUDA(cudaFree(h->linearStage));
+            BigFree(h->device, h->linearStage, h->linearStageFloats * sizeof(float));
             h->linearStage = nullptr;
             h->linearStageFloats = 0;
-            RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->linearStage), nFloats * sizeof(float)));
+            RT_CUDA(BigMalloc(h->device, reinterpret_cast<void**>(&h->linearStage), nFloats * sizeof(float)));
             h->linearStageFloats = nFloats;
         }
         if (srgb8 && h->srgbStageBytes < nFloats) {
-            if (h->srgbStage) RT_CUDA(cudaFree(h->srgbStage));
+            BigFree(h->device, h->srgbStage, h->srgbStageBytes);
             h->srgbStage = nullptr;
             h->srgbStageBytes = 0;
-            RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->srgbStage), nFloats));
+            RT_CUDA(BigMalloc(h->device, reinterpret_cast<void**>(&h->srgbStage), nFloats));
             h->srgbStageBytes = nFloats;
         }
         const int n = W * H;
@@ -1031,13 +1084,11 @@ int rt_scene_free(rt_scene_handle h)
 {
     if (!h) return RT_OK;
     cudaSetDevice(h->device);
-    for (void* p : h->allocations) cudaFree(p);
-    if (h->accum) cudaFree(h->accum);
-    if (h->linearStage) cudaFree(h->linearStage);
-    if (h->srgbStage) cudaFree(h->srgbStage);
-    if (h->stats) cudaFree(h->stats);
-    if (h->tileCounter) cudaFree(h->tileCounter);
-    if (h->debugOut) cudaFree(h->debugOut);
+    if (h->rendered) cudaStreamSynchronize(h->lastStream); // recycled buffers must be idle
+    BigFree(h->device, h->arena, h->arenaBytes);
+    BigFree(h->device, h->accum, h->accumFloats * sizeof(float));
+    BigFree(h->device, h->linearStage, h->linearStageFloats * sizeof(float));
+    BigFree(h->device, h->srgbStage, h->srgbStageBytes);
     delete h->host;
     delete h;
     return RT_OK;
@@ -1069,7 +1120,6 @@ int rt_debug_trace_path(rt_scene_handle h, const rt_camera* cam, const rt_render
         return RT_ERR_INVALID;
     }
     RT_CUDA(cudaSetDevice(h->device));
-    if (!h->debugOut) RT_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->debugOut), 256 * 8 * sizeof(float)));
     RT_CUDA(cudaMemset(h->debugOut, 0, 256 * 8 * sizeof(float)));
     h->debugPixel = pixel;
     h->debugSample = sample;
