@@ -61,6 +61,7 @@ struct RenderArgs {
     int tilesX, tilesY;
     // test hook (STATS instantiations only): per-bounce records of one (pixel, sample) path
     int waveSlots, waveIdleExit, waveLeafBatch, waveRefillMin; // wavefront variant tuning
+    int megaLeafMask; // megakernel: leaves are tested when (step & mask) == 0
     int stackLevels; // traversal stack entries per thread (BVH depth + 2, at most 32)
     int debugPixel, debugSample;
     float* debugOut; // [max_depth][8]: hit id, t, material, front, p.x, p.y, p.z, 1
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderMega(const DevS
     const int lane = threadIdx.x & 31;
     const int nTiles = args.tilesX * args.tilesY;
     const f3 background = make_f3(cam.background[0], cam.background[1], cam.background[2]);
+    const uint32_t leafMask = (uint32_t)args.megaLeafMask;
     unsigned long long nRays = 0, nPaths = 0, nNode = 0, nPrim = 0;
 
     while (true) {
@@ -226,10 +228,18 @@ __global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderMega(const DevS
                 }
             }
             if (__all_sync(0xffffffffu, done)) break;
+            // A lane that reaches a leaf waits for the warp's next leaf turn (every
+            // leafPeriod-th step): the FP64 primitive tests then run for all the lanes that
+            // piled up instead of for one or two lanes in nearly every step.
+            uint32_t step = 0;
             while (tv.ref != RT_TRAV_DONE) {
                 uint32_t nodeTests = 0, primTests = 0;
-                TraceStep<FEAT, SMEM>(sv, ray, slab, a, 0.001f, stack, tv, args.seed, pixel, (uint32_t)sample,
-                                      (uint32_t)bounce + 1u, nodeTests, primTests);
+                ++step;
+                if (!(tv.ref & RT_REF_LEAF))
+                    TraceBox<SMEM>(sv, slab, 0.001f, stack, tv, nodeTests);
+                else if ((step & leafMask) == 0u)
+                    TraceLeaf<FEAT, SMEM>(sv, ray, a, slab.rcpA, 0.001f, stack, tv, args.seed, pixel, (uint32_t)sample,
+                                          (uint32_t)bounce + 1u, primTests);
                 if (STATS) {
                     nNode += nodeTests;
                     nPrim += primTests;
@@ -428,7 +438,7 @@ __global__ void __launch_bounds__(512, 1) RenderWave(const DevScene scene, const
                 }
                 // the leaves that piled up, together
                 if ((tv.ref & RT_REF_LEAF) != 0u && tv.ref != RT_TRAV_DONE)
-                    TraceLeaf<FEAT, SMEM>(sv, ray, a, 0.001f, stack, tv, args.seed, myPixel, mySB >> 8, (mySB & 0xffu) + 1u,
+                    TraceLeaf<FEAT, SMEM>(sv, ray, a, slab.rcpA, 0.001f, stack, tv, args.seed, myPixel, mySB >> 8, (mySB & 0xffu) + 1u,
                                           primTests);
                 if (STATS) {
                     nNode += nodeTests;
@@ -930,6 +940,10 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     a.debugSample = h->debugSample;
     a.debugOut = h->debugPixel >= 0 ? h->debugOut : nullptr;
     // tiles: 8x4 pixels per warp (megakernel: one pixel per lane) or 8x8 (wavefront: 64 path slots)
+    // leaf turn every 2nd step (measured best: 1 -> 11.3, 2 -> 11.5, 4 -> 11.2 Grays/s); development knob in
+    // flags bits 4-5: 1 = every step, 2 = every 4th, 3 = every 8th
+    static const int kLeafMasks[4] = {1, 0, 3, 7};
+    a.megaLeafMask = kLeafMasks[(p->flags >> 4) & 3];
     // tuning knobs of the wavefront variant (development): flags bits 12-15 slots/32,
     // 16-20 idle-exit, 21-25 leaf batch, 26-30 refill minimum
     int waveSlots = ((p->flags >> 12) & 0xf) * 32;

@@ -155,6 +155,7 @@ struct DevCamera {
     double origin[3], llc[3], horiz[3], vert[3];
     double u[3], v[3];
     double lens_radius;
+    double inv_width, inv_height;
     float time0, time1;
     float background[3];
     int32_t width, height, max_depth;

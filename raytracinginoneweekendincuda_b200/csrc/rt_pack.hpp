@@ -400,7 +400,7 @@ inline void PackBox(const Box3& b, DevNode& n)
 {
     for (int a = 0; a < 3; ++a) {
         const double mag = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a]));
-        const double pad = 4e-7 * mag + 1e-7 * (b.hi[a] - b.lo[a]) + 1e-30;
+        const double pad = 8e-7 * mag + 2e-7 * (b.hi[a] - b.lo[a]) + 1e-30;
         n.lo[a] = RoundDown(b.lo[a] - pad);
         n.hi[a] = RoundUp(b.hi[a] + pad);
     }
@@ -801,6 +801,8 @@ inline DevCamera MakeCamera(const rt_camera& c)
         k.background[a] = (float)c.background[a];
     }
     k.lens_radius = aperture / 2.0;
+    k.inv_width = 1.0 / (double)c.image_width;
+    k.inv_height = 1.0 / (double)c.image_height;
     k.time0 = (float)c.time0;
     k.time1 = (float)c.time1;
     k.width = c.image_width;

@@ -47,6 +47,22 @@ RT_DEV f3 cross(f3 a, f3 b) { return make_f3(a.y * b.z - a.z * b.y, a.z * b.x - 
 // Vec3.h:117-120 with :96-99: v * (1/len)
 RT_DEV f3 unit(f3 a) { return (1.0f / sqrtf(dot(a, a))) * a; }
 
+// SFU approximations (1-2 ulp), one instruction each instead of the ~9 of an IEEE
+// division or root.  Used only where an FP64 refinement follows (roots of the
+// winning primitive) or where a conservative margin absorbs it (slab test).
+RT_DEV float RcpApprox(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+RT_DEV float SqrtApprox(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // FP64 vectors for the geometric chain hit point -> normal -> scattered
 // direction -> next hit point.  An fp32 link anywhere in that chain is a 6e-8
 // perturbation that diffuse inter-reflection between small spheres multiplies
@@ -71,7 +87,7 @@ RT_DEV f3 to_f3(d3 a) { return make_f3((float)a.x, (float)a.y, (float)a.z); }
 // (two for the reciprocal root) Newton steps: no FP64 division or root sequence.
 RT_DEV double RcpD(double x)
 {
-    const double r = (double)(1.0f / (float)x);
+    const double r = (double)RcpApprox((float)x);
     const double e = fma(-x, r, 1.0);
     return fma(fma(e, e, e), r, r);
 }
@@ -153,8 +169,9 @@ struct Ray {
 
 // What traversal needs besides the ray: fp32 copies for the slab test.
 struct RaySlab {
-    f3 inv; // 1/d
-    f3 ood; // o/d
+    f3 inv;     // 1/d
+    f3 ood;     // o/d
+    float rcpA; // 1/|d|^2, for the sphere roots
 };
 
 RT_DEV RaySlab MakeSlab(const Ray& r)
@@ -163,7 +180,8 @@ RT_DEV RaySlab MakeSlab(const Ray& r)
     const f3 df = make_f3((float)r.d.x, (float)r.d.y, (float)r.d.z);
     // AABB.h:77-93 divides by d; d == 0 gives +-inf and the NaNs of 0*inf are
     // dropped by fminf/fmaxf exactly as fmin/fmax do in the reference.
-    s.inv = make_f3(1.0f / df.x, 1.0f / df.y, 1.0f / df.z);
+    s.inv = make_f3(RcpApprox(df.x), RcpApprox(df.y), RcpApprox(df.z));
+    s.rcpA = RcpApprox(fmaf(df.x, df.x, fmaf(df.y, df.y, df.z * df.z)));
     s.ood = make_f3((float)r.o.x * s.inv.x, (float)r.o.y * s.inv.y, (float)r.o.z * s.inv.z);
     return s;
 }
@@ -190,36 +208,34 @@ RT_DEV float SlabEntry(const float4 lo, const float4 hi, const RaySlab& s, float
 // matters to 1e-3); the square root and the roots themselves are fp32 -- the
 // winner is refined by FinalizeSphere.  Root order and the open interval
 // (tmin, tmax) follow the reference.  Returns t or RT_MISS.
-RT_DEV float SphereRoots(double ocx, double ocy, double ocz, double radius, const Ray& r, double a, double tmin, float tmax)
+// TM = float for surface queries (tmin = 0.001), double for a medium's boundary
+// queries: its second one starts at t1 + 1e-4 (ConstantMedium.h:63), which fp32
+// cannot hold beyond t ~ 1000.  rcpA ~ 1/a.
+template <class TM>
+RT_DEV float SphereRoots(double ocx, double ocy, double ocz, double radius, const Ray& r, double a, float rcpA, TM tmin, float tmax)
 {
     const double b = fma(ocx, r.d.x, fma(ocy, r.d.y, ocz * r.d.z));
     const double c = fma(ocx, ocx, fma(ocy, ocy, fma(ocz, ocz, -radius * radius)));
     const double disc = fma(b, b, -a * c);
     if (!(disc > 0.0)) return RT_MISS;
-    const float s = sqrtf((float)disc);
-    const float bf = (float)b, cf = (float)c, af = (float)a;
-    // cancellation-free pair: q has the larger magnitude
-    const float q = bf > 0.0f ? -(bf + s) : (s - bf);
-    float t0, t1; // t0 <= t1
-    if (bf > 0.0f) {
-        t0 = q / af;
-        t1 = cf / q;
-    } else {
-        t0 = cf / q;
-        t1 = q / af;
-    }
-    // tmin is compared in FP64: a medium's second boundary query starts at
-    // t1 + 1e-4 (ConstantMedium.h:63), which fp32 cannot hold beyond t ~ 1000
-    if (t0 < tmax && (double)t0 > tmin) return t0;
-    if (t1 < tmax && (double)t1 > tmin) return t1;
+    const float s = SqrtApprox((float)disc);
+    const float bf = (float)b, cf = (float)c;
+    // cancellation-free pair: q has the larger magnitude; roots q/a and c/q
+    const bool pos = bf > 0.0f;
+    const float q = pos ? -(bf + s) : (s - bf);
+    const float ta = q * rcpA, tb = cf * RcpApprox(q);
+    const float t0 = pos ? ta : tb, t1 = pos ? tb : ta; // t0 <= t1
+    if (t0 < tmax && (TM)t0 > tmin) return t0;
+    if (t1 < tmax && (TM)t1 > tmin) return t1;
     return RT_MISS;
 }
 
-template <bool SMEM> RT_DEV float HitSphere(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, double tmin, float tmax)
+template <bool SMEM, class TM>
+RT_DEV float HitSphere(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float rcpA, TM tmin, float tmax)
 {
     const double2 s0 = LdD2<SMEM>(sv.spheres, index * 32u);
     const double2 s1 = LdD2<SMEM>(sv.spheres, index * 32u + 16u);
-    return SphereRoots(r.o.x - s0.x, r.o.y - s0.y, r.o.z - s1.x, s1.y, r, a, tmin, tmax);
+    return SphereRoots<TM>(r.o.x - s0.x, r.o.y - s0.y, r.o.z - s1.x, s1.y, r, a, rcpA, tmin, tmax);
 }
 
 // MovingSphere.h:44-102: centre lerped by the ray's time, then Sphere.
@@ -241,18 +257,19 @@ template <bool SMEM> RT_DEV d3 MovingCentre(const SceneView<SMEM>& sv, uint32_t 
     return c;
 }
 
-template <bool SMEM> RT_DEV float HitMoving(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, double tmin, float tmax)
+template <bool SMEM, class TM>
+RT_DEV float HitMoving(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float rcpA, TM tmin, float tmax)
 {
     double radius;
     const d3 c = MovingCentre<SMEM>(sv, index, r.time, radius);
-    return SphereRoots(r.o.x - c.x, r.o.y - c.y, r.o.z - c.z, radius, r, a, tmin, tmax);
+    return SphereRoots<TM>(r.o.x - c.x, r.o.y - c.y, r.o.z - c.z, radius, r, a, rcpA, tmin, tmax);
 }
 
 // Quad.h:54-99.  Plane terms in FP64, interior test in fp32.  Closed interval
 // [tmin, tmax] and closed [0,1] for alpha/beta as in the reference.  Returns t
 // or RT_MISS; alpha/beta are written on a hit.
-template <bool SMEM>
-RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double tmin, float tmax, float& alpha, float& beta)
+template <bool SMEM, class TM>
+RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, TM tmin, float tmax, float& alpha, float& beta)
 {
     const uint32_t off = index * 96u;
     const double2 q0 = LdD2<SMEM>(sv.quads, off);        // qx qy
@@ -263,8 +280,8 @@ RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, do
     const double denom = fma(q2.x, r.d.x, fma(q2.y, r.d.y, nz * r.d.z));
     if (fabs(denom) < 1e-8) return RT_MISS;
     const double num = q1.y - fma(q2.x, r.o.x, fma(q2.y, r.o.y, nz * r.o.z));
-    const float t = (float)num / (float)denom;
-    if ((double)t < tmin || t > tmax) return RT_MISS;
+    const float t = (float)num * RcpApprox((float)denom);
+    if ((TM)t < tmin || t > tmax) return RT_MISS;
     const float4 q4 = Ld4<SMEM>(sv.quads, off + 64u); // wz ux uy uz   (after wx wy in q3.y)
     const float4 q5 = Ld4<SMEM>(sv.quads, off + 80u); // vx vy vz mat
     const float wx = __int_as_float(__double2loint(q3.y)), wy = __int_as_float(__double2hiint(q3.y));
@@ -284,8 +301,9 @@ RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, do
 
 // One leaf-style run of primitives, closest hit with a shrinking tmax
 // (HittableList.h:39-57).  Returns the hit id or RT_HIT_NONE; t in tmax.
-template <int FEAT, bool SMEM>
-RT_DEV uint32_t HitRun(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, double a, double tmin, float& tmax, uint32_t& primTests)
+template <int FEAT, bool SMEM, class TM>
+RT_DEV uint32_t HitRun(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, double a, float rcpA, TM tmin, float& tmax,
+                       uint32_t& primTests)
 {
     const uint32_t type = RT_REF_TYPE(ref), first = RT_REF_FIRST(ref), count = RT_REF_COUNT(ref);
     uint32_t hit = RT_HIT_NONE;
@@ -294,11 +312,11 @@ RT_DEV uint32_t HitRun(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, do
         ++primTests;
         if ((FEAT & RT_FEAT_QUAD) && type == RT_LEAF_QUAD) {
             float al, be;
-            t = HitQuad<SMEM>(sv, first + i, r, tmin, tmax, al, be);
+            t = HitQuad<SMEM, TM>(sv, first + i, r, tmin, tmax, al, be);
         } else if ((FEAT & RT_FEAT_MOVING) && type == RT_LEAF_MOVING) {
-            t = HitMoving<SMEM>(sv, first + i, r, a, tmin, tmax);
+            t = HitMoving<SMEM, TM>(sv, first + i, r, a, rcpA, tmin, tmax);
         } else {
-            t = HitSphere<SMEM>(sv, first + i, r, a, tmin, tmax);
+            t = HitSphere<SMEM, TM>(sv, first + i, r, a, rcpA, tmin, tmax);
         }
         if (t != RT_MISS) {
             tmax = t;
@@ -336,7 +354,7 @@ RT_DEV double RefineSphereT(d3 c, double radius, const Ray& r, double a, float t
     const double td = (double)t;
     const double f = fma(fma(a, td, 2.0 * b), td, cc);
     const double fp = 2.0 * fma(a, td, b);
-    return td - (double)((float)f / (float)fp);
+    return td - (double)((float)f * RcpApprox((float)fp));
 }
 
 // t = (D - n.O)/(n.d) of a quad refined once in FP64 (Quad.h:62).
@@ -348,7 +366,7 @@ template <bool SMEM> RT_DEV double RefineQuadT(const SceneView<SMEM>& sv, uint32
     const double nz = LdD2<SMEM>(sv.quads, off + 48u).x;
     const double denom = fma(q2.x, r.d.x, fma(q2.y, r.d.y, nz * r.d.z));
     const double num = q1.y - fma(q2.x, r.o.x, fma(q2.y, r.o.y, nz * r.o.z));
-    const float invDen = 1.0f / (float)denom;
+    const float invDen = RcpApprox((float)denom);
     double td = (double)((float)num * invDen);
     td += (double)((float)fma(-td, denom, num) * invDen);
     td += (double)((float)fma(-td, denom, num) * invDen);
@@ -443,7 +461,7 @@ RT_DEV void FinalizeHit(const SceneView<SMEM>& sv, const Ray& r, double a, uint3
 // point is the origin of the rest of the path.  Returns true with the scatter
 // distance in tOut (always >= tmin > 0).
 template <int FEAT, bool SMEM>
-RT_DEV bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float tminF, float tmaxF,
+RT_DEV bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float rcpA, float tminF, float tmaxF,
                       uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests, double& tOut)
 {
     const float4 m0 = Ld4<SMEM>(sv.media, index * 32u);
@@ -452,13 +470,13 @@ RT_DEV bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, d
     const int visits = __float_as_int(m0.w);
     const float big = 3.402823466e+38f;
     float t1f = big;
-    const uint32_t h1 = HitRun<FEAT, SMEM>(sv, bref, r, a, -1.0e300, t1f, primTests);
+    const uint32_t h1 = HitRun<FEAT, SMEM, double>(sv, bref, r, a, rcpA, -1.0e300, t1f, primTests);
     if (h1 == RT_HIT_NONE) return false;
     const double t1 = RefineT<FEAT, SMEM>(sv, h1, r, a, t1f);
     float t2f = big;
     // the candidates of the second query are fp32 roots: the entry root must not pass
     // as "beyond t1 + 1e-4" because its fp32 value lies above the refined t1
-    const uint32_t h2 = HitRun<FEAT, SMEM>(sv, bref, r, a, fmax(t1, (double)t1f) + 0.0001, t2f, primTests);
+    const uint32_t h2 = HitRun<FEAT, SMEM, double>(sv, bref, r, a, rcpA, fmax(t1, (double)t1f) + 0.0001, t2f, primTests);
     if (h2 == RT_HIT_NONE) return false;
     const double t2 = RefineT<FEAT, SMEM>(sv, h2, r, a, t2f);
     const double negInvDensity = LdD2<SMEM>(sv.media, index * 32u + 16u).x;
@@ -539,34 +557,23 @@ RT_DEV void TraceBox(const SceneView<SMEM>& sv, const RaySlab& slab, float tmin,
 
 // One leaf: a typed run of primitives, or a medium.
 template <int FEAT, bool SMEM>
-RT_DEV void TraceLeaf(const SceneView<SMEM>& sv, const Ray& r, double a, float tmin, const Stack& stack, Trav& tv,
+RT_DEV void TraceLeaf(const SceneView<SMEM>& sv, const Ray& r, double a, float rcpA, float tmin, const Stack& stack, Trav& tv,
                       uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
 {
     const uint32_t ref = tv.ref;
     if ((FEAT & RT_FEAT_MEDIUM) && RT_REF_TYPE(ref) == RT_LEAF_MEDIUM) {
         const uint32_t m = RT_REF_FIRST(ref);
         double tm;
-        if (HitMedium<FEAT, SMEM>(sv, m, r, a, tmin, tv.t, seed, pixel, sample, slot, primTests, tm)) {
+        if (HitMedium<FEAT, SMEM>(sv, m, r, a, rcpA, tmin, tv.t, seed, pixel, sample, slot, primTests, tm)) {
             tv.t = (float)tm;
             tv.tMedium = tm;
             tv.hit = RT_HIT_MAKE(RT_LEAF_MEDIUM, m);
         }
     } else {
-        const uint32_t h = HitRun<FEAT, SMEM>(sv, ref, r, a, (double)tmin, tv.t, primTests);
+        const uint32_t h = HitRun<FEAT, SMEM, float>(sv, ref, r, a, rcpA, tmin, tv.t, primTests);
         if (h != RT_HIT_NONE) tv.hit = h;
     }
     TravPop(stack, tv);
-}
-
-template <int FEAT, bool SMEM>
-RT_DEV void TraceStep(const SceneView<SMEM>& sv, const Ray& r, const RaySlab& slab, double a, float tmin, const Stack& stack,
-                      Trav& tv, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& nodeTests,
-                      uint32_t& primTests)
-{
-    if (!(tv.ref & RT_REF_LEAF))
-        TraceBox<SMEM>(sv, slab, tmin, stack, tv, nodeTests);
-    else
-        TraceLeaf<FEAT, SMEM>(sv, r, a, tmin, stack, tv, seed, pixel, sample, slot, primTests);
 }
 
 // ----------------------------------------------------------------- textures
@@ -783,8 +790,8 @@ RT_DEV Ray CameraRay(const DevCamera& cam, int i, int j, const StreamKey& rng)
     rt_u4 b = rng.Block(0);
     const float fu = (float)i + rt_bits_to_u01(b.x);
     const float fv = (float)j + rt_bits_to_u01(b.y);
-    const double s = (double)fu / (double)cam.width;
-    const double t = (double)fv / (double)cam.height;
+    const double s = (double)fu * cam.inv_width; // kernel.cu:140-141 divides; the reciprocal is exact to 1 ulp of FP64
+    const double t = (double)fv * cam.inv_height;
     float px = 2.0f * rt_bits_to_u01(b.z) - 1.0f, py = 2.0f * rt_bits_to_u01(b.w) - 1.0f;
     uint32_t timeBits;
     if (px * px + py * py < 1.0f) {

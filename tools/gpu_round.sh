@@ -4,6 +4,8 @@
 TAG=${1:-r1}
 O=gpurun_out
 mkdir -p $O
+cp raytracinginoneweekendincuda_b200/librt_b200.so $O/librt_$TAG.so
+tar czf $O/src_$TAG.tgz raytracinginoneweekendincuda_b200/csrc include
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 $O/pytest_gpu_$TAG.log
 python bench.py > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench rc=$?"; cat $O/bench_$TAG.json; tail -3 $O/bench_$TAG.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$TAG.json 2>> $O/bench_$TAG.err; cat $O/bench_ref_$TAG.json
