@@ -153,6 +153,38 @@ def test_statistical_parity_against_oracle_noise_floor(oracle):
     assert np.sqrt(np.mean((g2 - o1 / spp) ** 2)) < 0.1 * noise
 
 
+def test_config2_full_size_4k_properties(oracle):
+    """BASELINE.json configs[1] at its full 3840x2160 (spp cut to 8 so it runs in a second):
+    size-independent properties.  (a) the samples split across 8 'GPUs' and summed equal the
+    single render up to fp32 summation order, ray for ray; (b) rays per path and the mean
+    radiance agree with the FP64 oracle rendered at 1/8 size (same camera, same statistics)."""
+    sc = BuiltinScene(10)
+    W, H, spp = 3840, 2160, 8
+    cam = sc.camera(W, H, spp, 50)
+    r = Renderer(sc.desc)
+    r.render(cam, 0, spp)
+    full, _, sf = r.readback()
+    for k in range(8):
+        r.render(cam, k, k + 1, clear=(k == 0))
+    parts, _, sp = r.readback()
+    info = r.info()
+    r.close()
+    assert info.scene_in_smem == 1
+    assert sp.rays == sf.rays
+    assert np.allclose(parts, full, rtol=3e-6, atol=1e-7)
+    assert np.isfinite(full).all() and full.min() >= 0.0
+    cam_s = sc.camera(W // 8, H // 8, spp, 50)
+    want, ost = oracle_render(oracle, sc, cam_s, 0, spp)
+    rpp_gpu, rpp_or = sf.rays / (W * H * spp), ost.rays / ost.paths
+    assert abs(rpp_gpu - rpp_or) < 0.01 * rpp_or, (rpp_gpu, rpp_or)
+    m_gpu, m_or = full.mean(axis=(0, 1), dtype=np.float64), (want / spp).mean(axis=(0, 1))  # fp32 mean of 8M drifts
+    assert np.allclose(m_gpu, m_or, rtol=0.01), (m_gpu, m_or)
+    # the 8x8 box-filtered 4K image is the small image up to Monte-Carlo noise
+    small = full.reshape(H // 8, 8, W // 8, 8, 3).mean(axis=(1, 3), dtype=np.float64)
+    rmse = np.sqrt(np.mean((small - want / spp) ** 2))
+    assert rmse < 0.1, rmse
+
+
 def _ref_gpu(args, env=None, cwd=None):
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu")
     if not os.path.exists(exe):
