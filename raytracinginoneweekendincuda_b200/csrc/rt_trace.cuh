@@ -186,16 +186,16 @@ RT_DEV RaySlab MakeSlab(const Ray& r)
     return s;
 }
 
-// AABB.h:68-98 as fused multiply-adds: t = lo*inv - o*inv.  Returns entry
-// distance, or +inf when the box is missed within [tmin, tmax].
-RT_DEV float SlabEntry(const float4 lo, const float4 hi, const RaySlab& s, float tmin, float tmax)
+// AABB.h:68-98 as fused multiply-adds: t = lo*inv - o*inv.  Returns whether the
+// box is hit within [tmin, tmax]; `tn` is the entry distance.
+RT_DEV bool SlabEntry(const float4 lo, const float4 hi, const RaySlab& s, float tmin, float tmax, float& tn)
 {
     const float x0 = fmaf(lo.x, s.inv.x, -s.ood.x), x1 = fmaf(hi.x, s.inv.x, -s.ood.x);
     const float y0 = fmaf(lo.y, s.inv.y, -s.ood.y), y1 = fmaf(hi.y, s.inv.y, -s.ood.y);
     const float z0 = fmaf(lo.z, s.inv.z, -s.ood.z), z1 = fmaf(hi.z, s.inv.z, -s.ood.z);
-    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
     const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
-    return tf >= tn ? tn : __int_as_float(0x7f800000);
+    return tf >= tn;
 }
 
 // ------------------------------------------------------------- primitives
@@ -540,10 +540,10 @@ RT_DEV void TraceBox(const SceneView<SMEM>& sv, const RaySlab& slab, float tmin,
     const float4 lo1 = Ld4<SMEM>(sv.nodes, off + 32u);
     const float4 hi1 = Ld4<SMEM>(sv.nodes, off + 48u);
     nodeTests += 2;
-    const float e0 = SlabEntry(lo0, hi0, slab, tmin, tv.t);
-    const float e1 = SlabEntry(lo1, hi1, slab, tmin, tv.t);
+    float e0, e1;
+    const bool h0 = SlabEntry(lo0, hi0, slab, tmin, tv.t, e0);
+    const bool h1 = SlabEntry(lo1, hi1, slab, tmin, tv.t, e1);
     const uint32_t r0 = (uint32_t)__float_as_int(lo0.w), r1 = (uint32_t)__float_as_int(lo1.w);
-    const bool h0 = e0 < 3.0e38f, h1 = e1 < 3.0e38f;
     if (h0 && h1) {
         const bool swap = e1 < e0;
         stack.Push(tv.sp++, swap ? r0 : r1);
