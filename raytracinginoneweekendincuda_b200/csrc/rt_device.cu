@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderMega(const DevS
         RaySlab slab = MakeSlab(ray);
         double a = 3.0;
         Trav tv;
-        tv.Begin(RT_TRAV_DONE);
+        tv.Idle();
         tv.tMedium = 0.0;
         int sample = args.sampleBegin;
         int bounce = 0;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderMega(const DevS
                 if (!done) {
                     slab = MakeSlab(ray);
                     a = fma(ray.d.x, ray.d.x, fma(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
-                    tv.Begin(sv.root_ref);
+                    tv.Begin(sv.root_ref, stack);
                 }
             }
             if (__all_sync(0xffffffffu, done)) break;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(512, 1) RenderWave(const DevScene scene, const
         RaySlab slab = MakeSlab(ray);
         double a = 3.0;
         Trav tv;
-        tv.Begin(RT_TRAV_DONE);
+        tv.Idle();
         tv.tMedium = 0.0;
         unsigned idleMask = FULL;
 
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(512, 1) RenderWave(const DevScene scene, const
                         myPixel = (uint32_t)((py0 + (s >> 3)) * cam.width + px0 + (s & 7));
                         slab = MakeSlab(ray);
                         a = fma(ray.d.x, ray.d.x, fma(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
-                        tv.Begin(sv.root_ref);
+                        tv.Begin(sv.root_ref, stack);
                     }
                     nReady -= take;
                     idleMask = __ballot_sync(FULL, mySlot < 0);
@@ -967,7 +967,7 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     int threads = p->block_threads > 0 ? p->block_threads : maxThreads;
     threads = std::max(32, std::min(maxThreads, (threads / 32) * 32));
     int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;
-    const int stackLevels = std::max(2, std::min(kMaxStackLevels, h->host->max_depth + 2));
+    const int stackLevels = std::max(3, std::min(kMaxStackLevels, h->host->max_depth + 3)); // + sentinel slot
     a.stackLevels = stackLevels;
     if (wave) {
         threads = std::min(threads, 512); // __launch_bounds__(512, 1)

@@ -717,7 +717,7 @@ struct Packer {
             root = b.BuildSah(ids, 0);
         }
         out.max_depth = b.maxDepth;
-        if (opt.bvh != RT_BVH_NONE && b.maxDepth > 30) throw std::invalid_argument("BVH deeper than the traversal stack");
+        if (opt.bvh != RT_BVH_NONE && b.maxDepth > 29) throw std::invalid_argument("BVH deeper than the traversal stack");
 
         // flatten: node 0 = root record, node 1 = pad, children pairs at even indices
         auto leafRef = [&](const BuildNode& n) -> uint32_t {

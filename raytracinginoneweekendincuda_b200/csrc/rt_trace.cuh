@@ -519,16 +519,25 @@ struct Trav {
     float t;      // closest hit so far (fp32; refined by FinalizeHit)
     uint32_t hit; // RT_HIT_* id or RT_HIT_NONE
     double tMedium; // FP64 scatter distance when `hit` is a medium
-    RT_DEV void Begin(uint32_t root)
+    // The bottom stack slot holds RT_TRAV_DONE, so popping never tests for an empty stack.
+    RT_DEV void Begin(uint32_t root, const Stack& stack)
     {
         ref = root;
+        stack.Push(0, RT_TRAV_DONE);
+        sp = 1;
+        t = 3.402823466e+38f;
+        hit = RT_HIT_NONE;
+    }
+    RT_DEV void Idle()
+    {
+        ref = RT_TRAV_DONE;
         sp = 0;
         t = 3.402823466e+38f;
         hit = RT_HIT_NONE;
     }
 };
 
-RT_DEV void TravPop(const Stack& stack, Trav& tv) { tv.ref = tv.sp == 0 ? RT_TRAV_DONE : stack.Pop(--tv.sp); }
+RT_DEV void TravPop(const Stack& stack, Trav& tv) { tv.ref = stack.Pop(--tv.sp); }
 
 // One internal node: both children boxes tested, nearer one entered first.
 template <bool SMEM>
