@@ -22,10 +22,14 @@
 
 // ---- BVH node: 32 bytes = two 128-bit loads.  Children of an internal node
 // are adjacent (index c and c+1), so one step fetches 64 contiguous bytes.
+// The box is stored as centre and half-extent: the slab test then needs no
+// per-axis min/max (entry/exit = t_centre -+ |e/d|), which moves 12 of its 20
+// min/max instructions per child pair from the half-rate ALU pipe -- the busiest
+// pipe of the kernel (ncu: 70 %) -- to the FMA pipe (20 %).
 struct RT_ALIGN(16) DevNode {
-    float lo[3];
+    float c[3];
     uint32_t ref; // what lies below this box: see RT_REF_*
-    float hi[3];
+    float e[3];
     uint32_t aux; // unused (0); keeps the record at 32 bytes
 };
 

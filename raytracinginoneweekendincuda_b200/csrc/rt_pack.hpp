@@ -395,14 +395,17 @@ inline float RoundUp(double v)
     return f;
 }
 
-// fp32 box that contains the FP64 box with a little slack for the fp32 slab test.
+// fp32 box, as centre and half-extent, that contains the FP64 box with a little
+// slack for the fp32 slab test (which measures entry/exit as t_centre -+ |e/d|).
 inline void PackBox(const Box3& b, DevNode& n)
 {
     for (int a = 0; a < 3; ++a) {
         const double mag = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a]));
         const double pad = 8e-7 * mag + 2e-7 * (b.hi[a] - b.lo[a]) + 1e-30;
-        n.lo[a] = RoundDown(b.lo[a] - pad);
-        n.hi[a] = RoundUp(b.hi[a] + pad);
+        const double lo = b.lo[a] - pad, hi = b.hi[a] + pad;
+        const float c = (float)(0.5 * (lo + hi));
+        n.c[a] = c;
+        n.e[a] = RoundUp(std::max(hi - (double)c, (double)c - lo));
     }
 }
 

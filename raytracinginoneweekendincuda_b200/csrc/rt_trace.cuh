@@ -186,15 +186,17 @@ RT_DEV RaySlab MakeSlab(const Ray& r)
     return s;
 }
 
-// AABB.h:68-98 as fused multiply-adds: t = lo*inv - o*inv.  Returns whether the
-// box is hit within [tmin, tmax]; `tn` is the entry distance.
-RT_DEV bool SlabEntry(const float4 lo, const float4 hi, const RaySlab& s, float tmin, float tmax, float& tn)
+// AABB.h:68-98 on a centre/half-extent box: per axis t_c = c*inv - o*inv and
+// p = e*inv, entry = t_c - |p|, exit = t_c + |p| (the |.| is a free source modifier
+// of FADD), so no per-axis min/max.  Returns whether the box is hit within
+// [tmin, tmax]; `tn` is the entry distance.
+RT_DEV bool SlabEntry(const float4 c, const float4 e, const RaySlab& s, float tmin, float tmax, float& tn)
 {
-    const float x0 = fmaf(lo.x, s.inv.x, -s.ood.x), x1 = fmaf(hi.x, s.inv.x, -s.ood.x);
-    const float y0 = fmaf(lo.y, s.inv.y, -s.ood.y), y1 = fmaf(hi.y, s.inv.y, -s.ood.y);
-    const float z0 = fmaf(lo.z, s.inv.z, -s.ood.z), z1 = fmaf(hi.z, s.inv.z, -s.ood.z);
-    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    const float cx = fmaf(c.x, s.inv.x, -s.ood.x), px = fabsf(e.x * s.inv.x);
+    const float cy = fmaf(c.y, s.inv.y, -s.ood.y), py = fabsf(e.y * s.inv.y);
+    const float cz = fmaf(c.z, s.inv.z, -s.ood.z), pz = fabsf(e.z * s.inv.z);
+    tn = fmaxf(fmaxf(cx - px, cy - py), fmaxf(cz - pz, tmin));
+    const float tf = fminf(fminf(cx + px, cy + py), fminf(cz + pz, tmax));
     return tf >= tn;
 }
 
