@@ -163,11 +163,11 @@ typedef struct rt_camera {
     double background[3];              /* constant colour (kernel.cu:77,197) */
 } rt_camera;
 
-/* Kernel variants (rt_render_params.variant). */
+/* Kernel variants (rt_render_params.variant).  Both render the same image bit for bit. */
 enum {
-    RT_VARIANT_AUTO = 0,      /* pick per scene class                          */
-    RT_VARIANT_MEGAKERNEL = 1, /* persistent-thread megakernel                  */
-    RT_VARIANT_WAVEFRONT = 2   /* ray-gen / extend / shade queues               */
+    RT_VARIANT_AUTO = 0,       /* the megakernel: measured faster on every scene */
+    RT_VARIANT_MEGAKERNEL = 1, /* persistent-thread megakernel                                    */
+    RT_VARIANT_WAVEFRONT = 2   /* on-chip wavefront: extend / shade / gen over warp-local queues  */
 };
 
 /* BVH the device traverses (rt_render_params.bvh / rt_upload_options.bvh). */
@@ -200,7 +200,9 @@ typedef struct rt_render_params {
 } rt_render_params;
 
 enum {
-    RT_FLAG_FP32_POSITIONS = 1 /* ablation: keep hit positions in fp32 (default FP64) */
+    RT_FLAG_STATS = 0x100,          /* instrumented kernel: fills rt_stats.paths/node_tests/prim_tests */
+    RT_FLAG_SCENE_IN_GLOBAL = 0x200 /* do not stage the scene in shared memory (A/B test)              */
+    /* bits 4-5 and 12-30 are development tuning knobs of the kernels (csrc/rt_device.cu)             */
 };
 
 typedef struct rt_scene_s* rt_scene_handle;
@@ -271,6 +273,8 @@ int rt_abi_sizeof(const char* name);
 
 /* Writes the reference's P3 text PPM (kernel.cu:696-723) from srgb8 (top row first). */
 int rt_write_ppm(const char* path, const uint8_t* srgb8, int32_t width, int32_t height);
+/* Same pixels as binary P6 (3 bytes per pixel instead of ~11 of text; not in the reference). */
+int rt_write_ppm_binary(const char* path, const uint8_t* srgb8, int32_t width, int32_t height);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,8 @@ RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_IMAGE, RT_TEX_NOISE = 0, 1, 2, 3
 RT_VARIANT_AUTO, RT_VARIANT_MEGAKERNEL, RT_VARIANT_WAVEFRONT = 0, 1, 2
 RT_BVH_SAH, RT_BVH_REFERENCE, RT_BVH_NONE = 0, 1, 2
-RT_FLAG_FP32_POSITIONS = 1
+RT_FLAG_STATS = 0x100
+RT_FLAG_SCENE_IN_GLOBAL = 0x200
 
 D3 = C.c_double * 3
 
@@ -156,6 +157,8 @@ def declare_device(lib: C.CDLL) -> None:
     lib.rt_rng_uniform.argtypes = [C.c_uint32] * 6
     lib.rt_write_ppm.restype = C.c_int
     lib.rt_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.rt_write_ppm_binary.restype = C.c_int
+    lib.rt_write_ppm_binary.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]
     lib.rt_debug_trace_path.restype = C.c_int
     lib.rt_debug_trace_path.argtypes = [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_params), C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_int32]

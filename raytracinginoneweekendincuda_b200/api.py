@@ -175,8 +175,9 @@ def render_scene(scene_id: int, width: int, height: int, spp: int, max_depth: in
     return lin, st
 
 
-def write_ppm(path: str, srgb8: np.ndarray) -> None:
-    """The reference's P3 text PPM (kernel.cu:696-723); srgb8 is [H,W,3], top row first."""
+def write_ppm(path: str, srgb8: np.ndarray, binary: bool = False) -> None:
+    """The reference's P3 text PPM (kernel.cu:696-723), or binary P6; srgb8 is [H,W,3], top row first."""
     lib = load_library()
     a = np.ascontiguousarray(srgb8, dtype=np.uint8)
-    _check(lib, lib.rt_write_ppm(path.encode(), a.ctypes.data, a.shape[1], a.shape[0]), "rt_write_ppm")
+    fn = lib.rt_write_ppm_binary if binary else lib.rt_write_ppm
+    _check(lib, fn(path.encode(), a.ctypes.data, a.shape[1], a.shape[0]), "rt_write_ppm")

@@ -6,6 +6,7 @@
 //
 //   rt_cli --scene 10 --width 1200 --height 675 --spp 10 --depth 50 --out out.ppm
 //          [--seed 1984] [--device 0] [--earth earthmap.rgb8 W H] [--bvh sah|reference|list]
+//          [--variant megakernel|wavefront] [--p6]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -26,6 +27,8 @@ int main(int argc, char** argv)
 {
     int sceneId = 9, width = 1440, height = 720, spp = -1, depth = 50, device = 0, bvh = RT_BVH_SAH;
     unsigned seed = 1984;
+    bool binary = false;
+    int variant = RT_VARIANT_AUTO;
     std::string out = "output.ppm", earthPath;
     int earthW = 0, earthH = 0;
     for (int i = 1; i < argc; ++i) {
@@ -49,6 +52,11 @@ int main(int argc, char** argv)
             earthPath = next("--earth");
             earthW = std::atoi(next("--earth W"));
             earthH = std::atoi(next("--earth H"));
+        } else if (a == "--p6") {
+            binary = true;
+        } else if (a == "--variant") {
+            const std::string v = next("--variant");
+            variant = v == "wavefront" ? RT_VARIANT_WAVEFRONT : (v == "megakernel" ? RT_VARIANT_MEGAKERNEL : RT_VARIANT_AUTO);
         } else if (a == "--bvh") {
             const std::string v = next("--bvh");
             bvh = v == "reference" ? RT_BVH_REFERENCE : (v == "list" ? RT_BVH_NONE : RT_BVH_SAH);
@@ -97,6 +105,7 @@ int main(int argc, char** argv)
     p.sample_end = spp;
     p.seed = seed;
     p.clear = 1;
+    p.variant = variant;
     const auto t0 = std::chrono::steady_clock::now();
     if (rt_render(scene, &cam, &p) != RT_OK) return Fail("rt_render");
     if (rt_sync(scene) != RT_OK) return Fail("rt_sync");
@@ -107,7 +116,8 @@ int main(int argc, char** argv)
     const double sec = std::chrono::duration<double>(t1 - t0).count();
     std::fprintf(stderr, "took %.4f seconds: %llu rays, %.1f Mrays/s.\n", sec, (unsigned long long)st.rays,
                  (double)st.rays / sec * 1e-6);
-    if (rt_write_ppm(out.c_str(), srgb.data(), width, height) != RT_OK) return Fail("rt_write_ppm");
+    if ((binary ? rt_write_ppm_binary : rt_write_ppm)(out.c_str(), srgb.data(), width, height) != RT_OK)
+        return Fail("rt_write_ppm");
     std::fprintf(stderr, "Done. Saved to %s\n", out.c_str());
     rt_scene_free(scene);
     return 0;

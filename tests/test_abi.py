@@ -70,3 +70,21 @@ def test_unknown_scene_id_is_an_error(lib):
     h = C.c_void_p()
     assert lib.rt_host_scene_builtin(77, None, 0, 0, C.byref(h)) == A.RT_ERR_INVALID
     assert b"unknown scene" in lib.rt_last_error()
+
+
+def test_ppm_writers_match_the_reference_format(lib, tmp_path):
+    """kernel.cu:696-723: 'P3\\nW H\\n255\\n' then 'r g b\\n' per pixel, top row first; P6 holds the same bytes.
+    Host-only code: runs without a GPU."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, size=(37, 53, 3), dtype=np.uint8)
+    img[0, 0] = (0, 9, 255)
+    p3, p6 = tmp_path / "a.ppm", tmp_path / "b.ppm"
+    assert lib.rt_write_ppm(str(p3).encode(), img.ctypes.data, 53, 37) == A.RT_OK
+    assert lib.rt_write_ppm_binary(str(p6).encode(), img.ctypes.data, 53, 37) == A.RT_OK
+    want = "P3\n53 37\n255\n" + "".join("%d %d %d\n" % tuple(px) for px in img.reshape(-1, 3))
+    assert p3.read_text() == want
+    raw = p6.read_bytes()
+    assert raw.startswith(b"P6\n53 37\n255\n") and raw[len(b"P6\n53 37\n255\n"):] == img.tobytes()
+    assert lib.rt_write_ppm(b"/nonexistent-dir/x.ppm", img.ctypes.data, 53, 37) == A.RT_ERR_INVALID
+    assert lib.rt_write_ppm(str(p3).encode(), None, 53, 37) == A.RT_ERR_INVALID

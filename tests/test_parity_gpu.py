@@ -260,6 +260,25 @@ def test_readback_srgb_and_ppm(tmp_path):
     assert len(lines) == 3 + 40 * 20 + 1
 
 
+def test_cli_writes_the_same_ppm_as_the_api(tmp_path):
+    """rt_cli = the reference's main() (kernel.cu:570-742) with flags, over the same C ABI."""
+    cli = os.path.join(ROOT, "raytracinginoneweekendincuda_b200", "rt_cli")
+    out = tmp_path / "cli.ppm"
+    res = subprocess.run([cli, "--scene", "10", "--width", "64", "--height", "36", "--spp", "3", "--out", str(out)],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "Mrays/s" in res.stderr
+    sc = BuiltinScene(10)
+    cam = sc.camera(64, 36, 3, 50)
+    r = Renderer(sc.desc)
+    r.render(cam)
+    _, s8, _ = r.readback(linear=False, srgb8=True)
+    r.close()
+    api = tmp_path / "api.ppm"
+    write_ppm(str(api), s8)
+    assert out.read_bytes() == api.read_bytes()
+
+
 def test_edge_cases_and_errors(lib):
     sc = BuiltinScene(10)
     r = Renderer(sc.desc)
