@@ -144,6 +144,25 @@ def cpu_baseline(budget_s=12.0):
                     if kind == "reference" else "oracle/rt_oracle.cpp (FP64 restatement), row-parallel std::thread"}
 
 
+def gpu_reference():
+    """The reference's own kernel.cu (FP64, cuRAND XORWOW, -arch=sm_100; oracle/_ref/ref_gpu, built by
+    oracle/build_ref.py with argv/ray-counter/event-timing patches) on this GPU, on a bounded sample of the
+    workload: the bar of BASELINE.json's ">= 10x the reference's CUDA kernel".  A reported baseline."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu")
+    if not os.path.exists(exe):
+        return None
+    spp = 8
+    try:
+        out = subprocess.run([exe, str(ARGS.width), str(ARGS.height), str(ARGS.scene), str(spp), str(SEED)],
+                             cwd=os.path.dirname(exe), capture_output=True, text=True, timeout=600)
+        row = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+    return {"value": row["mrays_per_s"], "unit": "Mrays/s", "kind": "reference kernel.cu on this GPU (Render only, CUDA events)",
+            "sample": f"{ARGS.width}x{ARGS.height}, {spp} of {ARGS.spp} spp, {row['rays']} rays in {row['render_ms']:.1f} ms",
+            "render_init_ms": row["render_init_ms"]}
+
+
 def run_reference_arm():
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -422,6 +441,7 @@ def run_b200_arm():
     }
     if world == 1 and not ARGS.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
+        line["gpu_reference"] = gpu_reference()
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local])

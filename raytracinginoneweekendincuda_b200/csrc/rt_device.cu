@@ -3,8 +3,11 @@
 // Replaces the reference's RenderInit + Render launches and the device-side
 // object graph they walk (reference kernel.cu:110-154, launched :681-689).
 //
+// Two kernels render the same image: RenderMega (default) and RenderWave (an
+// on-chip wavefront, kept for the comparison DESIGN.md 5.3 reports).
+//
 // Megakernel design (sm_100a, 148 SMs):
-//   * persistent CTAs, one per SM by default; each warp pulls 8x4-pixel tiles
+//   * persistent CTAs, one per SM, 768 threads; each warp pulls 8x4-pixel tiles
 //     from a global atomic counter, so long tiles do not stall a whole block
 //     the way the reference's 8x8 blocks do;
 //   * inside a tile every lane owns one pixel and runs a flat state machine
@@ -13,7 +16,7 @@
 //     of the warp finishes (the reference nests spp loop > bounce loop > BVH
 //     loop, kernel.cu:138-144 / :71-95 / BvhNode.h:113-155);
 //   * when nodes + primitives + materials fit, they are staged once per CTA in
-//     shared memory (Book 1: ~50 KB) and traversal runs on LDS.128; otherwise
+//     shared memory (Book 1: ~62 KB) and traversal runs on LDS.128; otherwise
 //     LDG.E.128 through the read-only path with the set resident in L1/L2;
 //   * the traversal stack lives in shared memory, [level][thread];
 //   * no per-pixel RNG state: every uniform is a hash of
@@ -59,10 +62,10 @@ struct RenderArgs {
     int sampleBegin, sampleEnd;
     uint32_t seed;
     int tilesX, tilesY;
-    // test hook (STATS instantiations only): per-bounce records of one (pixel, sample) path
     int waveSlots, waveIdleExit, waveLeafBatch, waveRefillMin; // wavefront variant tuning
     int megaLeafMask; // megakernel: leaves are tested when (step & mask) == 0
-    int stackLevels; // traversal stack entries per thread (BVH depth + 2, at most 32)
+    int stackLevels;  // traversal stack entries per thread (BVH depth + 3, at most 32)
+    // test hook (STATS instantiations only): per-bounce records of one (pixel, sample) path
     int debugPixel, debugSample;
     float* debugOut; // [max_depth][8]: hit id, t, material, front, p.x, p.y, p.z, 1
     // byte sizes of the staged arrays (SMEM variant)
