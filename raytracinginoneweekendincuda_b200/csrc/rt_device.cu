@@ -953,9 +953,9 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     a.waveIdleExit = (p->flags >> 16) & 0x1f;
     a.waveLeafBatch = (p->flags >> 21) & 0x1f;
     a.waveRefillMin = (p->flags >> 26) & 0x1f;
-    if (a.waveIdleExit <= 0) a.waveIdleExit = 12;
-    if (a.waveLeafBatch <= 0) a.waveLeafBatch = 12;
-    if (a.waveRefillMin <= 0) a.waveRefillMin = 6;
+    if (a.waveIdleExit <= 0) a.waveIdleExit = 16;
+    if (a.waveLeafBatch <= 0) a.waveLeafBatch = 16;
+    if (a.waveRefillMin <= 0) a.waveRefillMin = 8;
     auto pad16 = [](size_t b) { return (uint32_t)((b + 15) / 16 * 16); };
     const rtpack::Packed& pk = *h->host;
     a.nodesBytes = pad16(std::max<size_t>(1, pk.nodes.size()) * sizeof(DevNode));
@@ -979,16 +979,10 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     const size_t stackBytes = (size_t)threads * 4 * stackLevels;
     size_t poolBytes = 0;
     if (wave) {
-        // largest pool (more slots = fuller SHADE/GEN chunks) that still leaves room for the scene
+        // 64 slots (an 8x8 tile) measured best: 96 or 128 fill SHADE/GEN chunks better but cost more shared
+        // memory traffic and longer tile tails (profiles/r1_wavefront_parameter_sweep.json)
         auto bytesFor = [&](int slots) { return (size_t)(threads / 32) * PoolBytes(slots) + 16; };
-        if (waveSlots < 64 || waveSlots > 128) {
-            waveSlots = 64;
-            for (int cand : {128, 96})
-                if (stackBytes + bytesFor(cand) + h->stagedBytes <= (size_t)h->maxSmemOptin) {
-                    waveSlots = cand;
-                    break;
-                }
-        }
+        if (waveSlots < 64 || waveSlots > 128) waveSlots = 64;
         poolBytes = bytesFor(waveSlots);
     }
     a.waveSlots = waveSlots;
