@@ -910,6 +910,10 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
         return RT_ERR_INVALID;
     }
     const bool wave = p->variant == RT_VARIANT_WAVEFRONT;
+    if (wave && p->sample_end >= (1 << 24)) { // its slots pack sample << 8 | bounce
+        rt_set_error("rt_render: the wavefront variant takes sample indices below 2^24");
+        return RT_ERR_INVALID;
+    }
     RT_CUDA(cudaSetDevice(h->device));
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
     const size_t nFloats = (size_t)cam->image_width * cam->image_height * 3;
