@@ -277,6 +277,8 @@ def run_b200_arm():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; keep stdout = one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
