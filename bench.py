@@ -40,6 +40,10 @@ SEED = 1984
 # algorithmic work per ray on the REFERENCE-topology BVH
 FLOP_BOX, FLOP_SPHERE, FLOP_QUAD, FLOP_SHADE = 24.0, 30.0, 28.0, 120.0
 BYTES_NODE = 32.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one RenderMega launch on the 4K frame, from the
+# `ncu --set full` capture summarised in profiles/r1_RenderMega_book1_raw_selected.txt (99.9 MB + 50.3 MB):
+# the fp32 accumulator, read-modify-written once per pixel per launch, whatever the spp.
+NCU_DRAM_BYTES_4K_LAUNCH = 99915520 + 50284800
 
 
 def parse_args():
@@ -420,7 +424,8 @@ def run_b200_arm():
     hbm_bytes = H * W * 3 * 4 * 2  # accumulator read-modify-write, once per pixel per launch
     roofline = {
         "bound": "fp32", "kernel": "RenderMega", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-        "frac": achieved / peak.value if peak.value else None, "traffic": None,
+        "frac": achieved / peak.value if peak.value else None,
+        "traffic": NCU_DRAM_BYTES_4K_LAUNCH if (W, H) == (3840, 2160) else None,
         "peak_source": "FFMA microbenchmark run live on this GPU (rt_measure_fp32_peak); MEASURED_PEAKS.json "
                        "holds only HBM and bf16-tensor peaks, neither of which bounds this path",
         "flop_per_ray": flop_ray, "l1_bytes_per_ray": bytes_ray, "reference_topology": topo,
