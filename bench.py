@@ -281,9 +281,19 @@ def run_b200_arm():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; keep stdout = one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator is created: send stdout to
+        # stderr while that happens, so that stdout carries the one JSON line and nothing else
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
@@ -431,11 +441,17 @@ def run_b200_arm():
         "flop_per_ray": flop_ray, "l1_bytes_per_ray": bytes_ray, "reference_topology": topo,
         "kernel_ms": kernel_ms_max, "rays_per_launch": rays_kernel,
         "grays_per_s_kernel": rays_kernel / (kernel_ms_max * 1e-3) / 1e9,
+        # secondary bound of SURVEY 8(d): node/primitive fetches (algorithmic bytes on the reference topology)
+        # against the shared-memory/L1 bandwidth, nominal 128 B/clk/SM at the clock seen during the run
+        "l1": {"achieved": rays_kernel * bytes_ray / (kernel_ms_max * 1e-3) / 1e9, "unit": "GB/s",
+               "peak": sms.value * 128.0 * ((clk or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+               "peak_source": "nominal: SMs x 128 B/clk x sampled SM clock (not measured)"},
         "hbm": {"achieved": hbm_bytes / (kernel_ms_max * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_bytes / (kernel_ms_max * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                 "algorithmic_bytes_per_launch": hbm_bytes},
     }
+    roofline["l1"]["frac"] = roofline["l1"]["achieved"] / roofline["l1"]["peak"]
     line = {
         "metric": "Mrays/s incl. secondary rays", "value": value, "unit": "Mrays/s", "n_gpus": world,
         "steps": ARGS.steps, "warmup": ARGS.warmup, "ms_per_step": ms_step, "ms_per_frame": ms_step,
