@@ -8,7 +8,7 @@ from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, load_earth
 sid = int(os.environ.get("SCENE", "10"))
 W, H, spp = (int(x) for x in os.environ.get("SIZE", "3840,2160,16").split(","))
 sc = BuiltinScene(sid, load_earth_fixture() if sid in (2, 9) else None)
-cam = sc.camera(W, H, spp, 50)
+cam = sc.camera(W, H, spp, int(os.environ.get("DEPTH", "50")))
 r = Renderer(sc.desc, max_leaf_prims=int(os.environ.get('LEAF', '0')))
 stream = torch.cuda.current_stream().cuda_stream
 for f in sys.argv[1:]:
