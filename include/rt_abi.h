@@ -167,7 +167,8 @@ typedef struct rt_camera {
 enum {
     RT_VARIANT_AUTO = 0,       /* the megakernel: measured faster on every scene */
     RT_VARIANT_MEGAKERNEL = 1, /* persistent-thread megakernel                                    */
-    RT_VARIANT_WAVEFRONT = 2   /* on-chip wavefront: extend / shade / gen over warp-local queues  */
+    RT_VARIANT_WAVEFRONT = 2,  /* on-chip wavefront: extend / shade / gen over warp-local queues  */
+    RT_VARIANT_HEADTAIL = 3    /* synchronous heads (new samples) + queued tails (continuations)   */
 };
 
 /* BVH the device traverses (rt_render_params.bvh / rt_upload_options.bvh). */

@@ -21,7 +21,7 @@ RT_XFORM_TRANSLATE, RT_XFORM_ROTATE_Y = 0, 1
 RT_OBJ_PRIM, RT_OBJ_LIST, RT_OBJ_MEDIUM = 0, 1, 2
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = 0, 1, 2, 3, 4
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_IMAGE, RT_TEX_NOISE = 0, 1, 2, 3
-RT_VARIANT_AUTO, RT_VARIANT_MEGAKERNEL, RT_VARIANT_WAVEFRONT = 0, 1, 2
+RT_VARIANT_AUTO, RT_VARIANT_MEGAKERNEL, RT_VARIANT_WAVEFRONT, RT_VARIANT_HEADTAIL = 0, 1, 2, 3
 RT_BVH_SAH, RT_BVH_REFERENCE, RT_BVH_NONE = 0, 1, 2
 RT_FLAG_STATS = 0x100
 RT_FLAG_SCENE_IN_GLOBAL = 0x200

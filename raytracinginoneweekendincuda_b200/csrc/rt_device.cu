@@ -606,6 +606,240 @@ __global__ void __launch_bounds__(512, 1) RenderWave(const DevScene scene, const
     }
 }
 
+// ---------------------------------------------------------------------------
+// Head/tail variant.  Measured on the megakernel (profiles/README.md): when every
+// lane of a warp is at the same bounce -- max_depth 1 or 2 -- it runs 25 / 22
+// Grays/s instead of 13.5, because camera rays are generated on full warps, the
+// coherent primary rays of 32 neighbouring pixels finish their walks together,
+// and every lane has something to shade.  This kernel keeps that synchrony
+// without idling lanes whose path is over:
+//   HEAD  all 32 lanes start the SAME sample of their pixels: camera ray, walk,
+//         shade.  Paths that go on are not continued by their lane: their state
+//         (ray, throughput, owner, sample, bounce: 64 B) is pushed on the warp's
+//         queue in shared memory (ballot + popc compaction).
+//   TAIL  whenever the queue holds 32 continuations, one round takes 32 of them:
+//         one ray each, walk, shade, push back what survives.  Every round runs
+//         on a full warp whatever the path lengths are.
+// Radiance goes to per-pixel sums in shared memory (a tail adds to its owner's
+// sum; two tails of one owner in a round are serialised in lane order, so the
+// result is deterministic).  The order in which a pixel's paths are summed is no
+// longer the sample order, so images equal the megakernel's up to fp32
+// summation order, not bit for bit.
+constexpr int kHtQueue = 64; // entries per warp
+__host__ __device__ constexpr int HtWarpBytes(int feat)
+{
+    return kHtQueue * (6 * 8 + 3 * 4 + 4 + ((feat & RT_FEAT_MOVING) ? 4 : 0)) + 32 * 3 * 4;
+}
+#define RT_HT_MAX_SAMPLES (1 << 19) /* sample index relative to sample_begin is packed in 19 bits */
+
+template <int FEAT, bool SMEM, bool STATS>
+__global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderHeadTail(const DevScene scene, const DevCamera cam, const RenderArgs args)
+{
+    extern __shared__ __align__(16) char smem[];
+    const uint32_t smemBase = SmemAddr(smem);
+    uint32_t cursor = blockDim.x * 4u * (uint32_t)args.stackLevels;
+    const SceneView<SMEM> sv = SetupScene<SMEM>(scene, args, smem, smemBase, cursor);
+
+    Stack stack;
+    stack.base = smemBase + threadIdx.x * 4u;
+    stack.stride = blockDim.x * 4u;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu, ltMask = (1u << lane) - 1u;
+    char* wbase = smem + ((cursor + 15u) & ~15u) + (uint32_t)warp * (uint32_t)HtWarpBytes(FEAT);
+    double* QO = reinterpret_cast<double*>(wbase);            // [3][64]
+    double* QD = QO + 3 * kHtQueue;                           // [3][64]
+    float* QTHR = reinterpret_cast<float*>(QD + 3 * kHtQueue); // [3][64]
+    uint32_t* QMETA = reinterpret_cast<uint32_t*>(QTHR + 3 * kHtQueue); // owner | bounce << 5 | (sample - begin) << 13
+    float* QTIME = reinterpret_cast<float*>(QMETA + kHtQueue);          // [64], FEAT_MOVING only
+    float* SUM = QTIME + ((FEAT & RT_FEAT_MOVING) ? kHtQueue : 0);      // [3][32]
+
+    const int nTiles = args.tilesX * args.tilesY;
+    const f3 background = make_f3(cam.background[0], cam.background[1], cam.background[2]);
+    const uint32_t leafMask = (uint32_t)args.megaLeafMask;
+    unsigned long long nRays = 0, nPaths = 0, nNode = 0, nPrim = 0;
+
+    while (true) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(args.tileCounter, 1u);
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= nTiles) break;
+        const int px0 = (tile % args.tilesX) * kTileW, py0 = (tile / args.tilesX) * kTileH;
+        const bool valid = px0 + (lane & (kTileW - 1)) < cam.width && py0 + lane / kTileW < cam.height;
+        SUM[lane] = SUM[32 + lane] = SUM[64 + lane] = 0.0f;
+        __syncwarp();
+        int nQ = 0;
+        int headSample = args.sampleBegin;
+
+        while (headSample < args.sampleEnd || nQ > 0) {
+            // A round is a TAIL round when the queue could not take the survivors of another head
+            // (or when there are no heads left); else a HEAD round.
+            const bool tailRound = nQ > kHtQueue - 32 || headSample >= args.sampleEnd;
+            Ray ray;
+            f3 thr;
+            uint32_t owner = (uint32_t)lane, sample = 0, bounce = 0;
+            bool active;
+            if (tailRound) {
+                const int n = min(nQ, 32);
+                active = lane < n;
+                if (active) {
+                    const int e = nQ - n + lane;
+                    ray.o = make_d3(QO[e], QO[kHtQueue + e], QO[2 * kHtQueue + e]);
+                    ray.d = make_d3(QD[e], QD[kHtQueue + e], QD[2 * kHtQueue + e]);
+                    ray.time = (FEAT & RT_FEAT_MOVING) ? QTIME[e] : 0.0f;
+                    thr = make_f3(QTHR[e], QTHR[kHtQueue + e], QTHR[2 * kHtQueue + e]);
+                    const uint32_t meta = QMETA[e];
+                    owner = meta & 31u;
+                    bounce = (meta >> 5) & 0xffu;
+                    sample = (uint32_t)args.sampleBegin + (meta >> 13);
+                }
+                nQ -= n;
+                __syncwarp(); // all entries are read before any survivor is written back
+            } else {
+                active = valid;
+                sample = (uint32_t)headSample;
+                ++headSample;
+            }
+            const int oi = px0 + (int)(owner & (kTileW - 1)), oj = py0 + (int)(owner / kTileW);
+            const uint32_t pixel = (uint32_t)(oj * cam.width + oi);
+            if (!tailRound && active) {
+                const StreamKey rng = MakeKey(args.seed, pixel, sample, 0u);
+                ray = CameraRay(cam, oi, oj, rng);
+                thr = make_f3(1.0f, 1.0f, 1.0f);
+                if (STATS) ++nPaths;
+            }
+
+            // one ray per lane, walked to completion
+            Trav tv;
+            tv.Idle();
+            tv.tMedium = 0.0;
+            RaySlab slab;
+            double a = 1.0;
+            if (active) {
+                slab = MakeSlab(ray);
+                a = fma(ray.d.x, ray.d.x, fma(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
+                tv.Begin(sv.root_ref, stack);
+                ++nRays;
+            }
+            uint32_t step = 0;
+            while (tv.ref != RT_TRAV_DONE) {
+                uint32_t nodeTests = 0, primTests = 0;
+                ++step;
+                if (!(tv.ref & RT_REF_LEAF))
+                    TraceBox<SMEM>(sv, slab, 0.001f, stack, tv, nodeTests);
+                else if ((step & leafMask) == 0u)
+                    TraceLeaf<FEAT, SMEM>(sv, ray, a, slab.rcpA, 0.001f, stack, tv, args.seed, pixel, sample, bounce + 1u,
+                                          primTests);
+                if (STATS) {
+                    nNode += nodeTests;
+                    nPrim += primTests;
+                }
+            }
+
+            // shade
+            f3 add = make_f3(0.0f, 0.0f, 0.0f);
+            bool hasAdd = false, survives = false;
+            d3 newO = ray.o, newD = ray.d;
+            if (active) {
+                if (tv.hit == RT_HIT_NONE) {
+                    add = thr * background; // kernel.cu:74-79
+                    hasAdd = true;
+                } else {
+                    Hit h;
+                    FinalizeHit<FEAT, SMEM>(sv, ray, a, tv.hit, tv.t, tv.tMedium, h);
+                    const uint32_t type = RT_HIT_TYPE(tv.hit);
+                    if (STATS && args.debugOut && (int)pixel == args.debugPixel && (int)sample == args.debugSample) {
+                        float* o = args.debugOut + bounce * 8;
+                        o[0] = __uint_as_float(tv.hit);
+                        o[1] = tv.t;
+                        o[2] = __int_as_float(h.material);
+                        o[3] = h.front ? 1.0f : 0.0f;
+                        o[4] = (float)h.p.x;
+                        o[5] = (float)h.p.y;
+                        o[6] = (float)h.p.z;
+                        o[7] = 1.0f;
+                    }
+                    const bool sphereLike = type == RT_LEAF_SPHERE || type == RT_LEAF_MOVING;
+                    const StreamKey rng = MakeKey(args.seed, pixel, sample, bounce + 1u);
+                    f3 atten, emitted;
+                    d3 dir;
+                    const bool scattered = Scatter<FEAT, SMEM>(sv, h, ray.d, a, sphereLike, rng, atten, dir, emitted);
+                    if (!scattered) { // kernel.cu:82-83: emission is black unless the path ends on a light
+                        add = thr * emitted;
+                        hasAdd = emitted.x != 0.0f || emitted.y != 0.0f || emitted.z != 0.0f;
+                    } else if ((int)bounce + 1 < cam.max_depth) { // kernel.cu:93-94, :71
+                        thr = thr * atten;
+                        newO = h.p;
+                        newD = dir;
+                        survives = true;
+                    }
+                }
+            }
+
+            // radiance to the owner's sum; two contributions to one owner are applied in lane order
+            {
+                const unsigned am = __ballot_sync(FULL, hasAdd);
+                int rank = 0;
+                if (hasAdd) rank = __popc(__match_any_sync(am, owner) & ltMask);
+                for (int r = 0;; ++r) {
+                    if (hasAdd && rank == r) {
+                        SUM[owner] += add.x;
+                        SUM[32 + owner] += add.y;
+                        SUM[64 + owner] += add.z;
+                    }
+                    __syncwarp();
+                    if (__ballot_sync(FULL, hasAdd && rank > r) == 0u) break;
+                }
+            }
+            // survivors back on the queue
+            {
+                const unsigned sm_ = __ballot_sync(FULL, survives);
+                if (survives) {
+                    const int e = nQ + __popc(sm_ & ltMask);
+                    QO[e] = newO.x;
+                    QO[kHtQueue + e] = newO.y;
+                    QO[2 * kHtQueue + e] = newO.z;
+                    QD[e] = newD.x;
+                    QD[kHtQueue + e] = newD.y;
+                    QD[2 * kHtQueue + e] = newD.z;
+                    QTHR[e] = thr.x;
+                    QTHR[kHtQueue + e] = thr.y;
+                    QTHR[2 * kHtQueue + e] = thr.z;
+                    if (FEAT & RT_FEAT_MOVING) QTIME[e] = ray.time;
+                    QMETA[e] = owner | ((bounce + 1u) << 5) | ((sample - (uint32_t)args.sampleBegin) << 13);
+                }
+                nQ += __popc(sm_);
+                __syncwarp();
+            }
+        }
+
+        if (valid) {
+            float* px = args.accum + ((size_t)(py0 + lane / kTileW) * cam.width + px0 + (lane & (kTileW - 1))) * 3u;
+            px[0] += SUM[lane];
+            px[1] += SUM[32 + lane];
+            px[2] += SUM[64 + lane];
+        }
+        __syncwarp();
+    }
+
+    for (int off = 16; off > 0; off >>= 1) {
+        nRays += __shfl_down_sync(FULL, nRays, off);
+        if (STATS) {
+            nPaths += __shfl_down_sync(FULL, nPaths, off);
+            nNode += __shfl_down_sync(FULL, nNode, off);
+            nPrim += __shfl_down_sync(FULL, nPrim, off);
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&args.stats[0], nRays);
+        if (STATS) {
+            atomicAdd(&args.stats[1], nPaths);
+            atomicAdd(&args.stats[2], nNode);
+            atomicAdd(&args.stats[3], nPrim);
+        }
+    }
+}
+
 // kernel.cu:147-153 (mean, sqrt gamma) + :712-718 (clamp to [0,0.999], *256),
 // fused with the row flip to PPM order (kernel.cu:699: top row first).
 __global__ void ResolveKernel(const float* __restrict__ accum, float* __restrict__ linearOut, uint8_t* __restrict__ srgbOut,
@@ -655,8 +889,13 @@ __global__ void FmaPeakKernel(float* out, int iters)
 
 using KernelFn = void (*)(const DevScene, const DevCamera, const RenderArgs);
 
-template <int FEAT> KernelFn PickKernel(bool wave, bool smem, bool stats)
+template <int FEAT> KernelFn PickKernel(int variant, bool smem, bool stats)
 {
+    const bool wave = variant == RT_VARIANT_WAVEFRONT;
+    if (variant == RT_VARIANT_HEADTAIL) {
+        if (smem) return stats ? RenderHeadTail<FEAT, true, true> : RenderHeadTail<FEAT, true, false>;
+        return stats ? RenderHeadTail<FEAT, false, true> : RenderHeadTail<FEAT, false, false>;
+    }
     if (wave) {
         if (smem) return stats ? RenderWave<FEAT, true, true> : RenderWave<FEAT, true, false>;
         return stats ? RenderWave<FEAT, false, true> : RenderWave<FEAT, false, false>;
@@ -670,18 +909,18 @@ constexpr int kFeatSpheres = 0;
 constexpr int kFeatMotion = RT_FEAT_MOVING | RT_FEAT_TEXTURE;
 constexpr int kFeatAll = RT_FEAT_MOVING | RT_FEAT_QUAD | RT_FEAT_MEDIUM | RT_FEAT_TEXTURE;
 
-KernelFn PickKernelForFeatures(int features, bool wave, bool smem, bool stats, int* picked)
+KernelFn PickKernelForFeatures(int features, int variant, bool smem, bool stats, int* picked)
 {
     if (features == 0) {
         *picked = kFeatSpheres;
-        return PickKernel<kFeatSpheres>(wave, smem, stats);
+        return PickKernel<kFeatSpheres>(variant, smem, stats);
     }
     if ((features & ~kFeatMotion) == 0) {
         *picked = kFeatMotion;
-        return PickKernel<kFeatMotion>(wave, smem, stats);
+        return PickKernel<kFeatMotion>(variant, smem, stats);
     }
     *picked = kFeatAll;
-    return PickKernel<kFeatAll>(wave, smem, stats);
+    return PickKernel<kFeatAll>(variant, smem, stats);
 }
 
 // Frame-sized device buffers (accumulator, readback staging) are recycled across
@@ -905,11 +1144,16 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
         rt_set_error("rt_render: image too large");
         return RT_ERR_INVALID;
     }
-    if (p->variant < RT_VARIANT_AUTO || p->variant > RT_VARIANT_WAVEFRONT) {
+    if (p->variant < RT_VARIANT_AUTO || p->variant > RT_VARIANT_HEADTAIL) {
         rt_set_error("rt_render: unknown variant %d", p->variant);
         return RT_ERR_INVALID;
     }
     const bool wave = p->variant == RT_VARIANT_WAVEFRONT;
+    const bool headTail = p->variant == RT_VARIANT_HEADTAIL;
+    if (headTail && (long long)p->sample_end - p->sample_begin > RT_HT_MAX_SAMPLES) {
+        rt_set_error("rt_render: the head/tail variant takes at most %d samples per call", RT_HT_MAX_SAMPLES);
+        return RT_ERR_INVALID;
+    }
     if (wave && p->sample_end >= (1 << 24)) { // its slots pack sample << 8 | bounce
         rt_set_error("rt_render: the wavefront variant takes sample indices below 2^24");
         return RT_ERR_INVALID;
@@ -980,8 +1224,18 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
         threads = std::min(threads, 512); // __launch_bounds__(512, 1)
         blocksPerSm = 1;
     }
+    const int featClass = h->dev.features == 0 ? kFeatSpheres : ((h->dev.features & ~kFeatMotion) == 0 ? kFeatMotion : kFeatAll);
+    if (headTail && p->block_threads <= 0 && !(p->flags & 0x200)) {
+        // the largest block whose stacks + queues still leave room for the scene in shared memory
+        for (int cand = maxThreads; cand >= 256; cand -= 128) {
+            threads = cand;
+            if ((size_t)cand * 4 * stackLevels + (size_t)(cand / 32) * HtWarpBytes(featClass) + 16 + h->stagedBytes <=
+                (size_t)h->maxSmemOptin)
+                break;
+        }
+    }
     const size_t stackBytes = (size_t)threads * 4 * stackLevels;
-    size_t poolBytes = 0;
+    size_t poolBytes = headTail ? (size_t)(threads / 32) * HtWarpBytes(featClass) + 16 : 0;
     if (wave) {
         // 64 slots (an 8x8 tile) measured best: 96 or 128 fill SHADE/GEN chunks better but cost more shared
         // memory traffic and longer tile tails (profiles/r1_wavefront_parameter_sweep.json)
@@ -1002,7 +1256,7 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
                      h->maxSmemOptin);
         return RT_ERR_INVALID;
     }
-    KernelFn fn = PickKernelForFeatures(h->dev.features, wave, smem, wantStats, &h->pickedFeatures);
+    KernelFn fn = PickKernelForFeatures(h->dev.features, p->variant, smem, wantStats, &h->pickedFeatures);
     RT_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     const int nTiles = a.tilesX * a.tilesY;
     const int warpsPerBlock = threads / 32;

@@ -104,6 +104,20 @@ def test_wavefront_variant_renders_the_same_image_as_the_megakernel(earth, sid, 
     assert (a == b).mean() > 0.999
 
 
+@pytest.mark.parametrize("sid,W,H,spp", [(10, 200, 113, 6), (0, 96, 54, 4), (7, 64, 64, 6), (8, 64, 64, 6), (9, 96, 54, 3)])
+def test_headtail_variant_renders_the_same_image_as_the_megakernel(earth, sid, W, H, spp):
+    """Same rays, same device functions; a pixel's paths are summed in completion order instead of
+    sample order, so equality holds up to fp32 summation order."""
+    sc = scene_for(sid, earth)
+    cam = sc.camera(W, H, spp, 50)
+    a, sa, _ = gpu_render(sc, cam, variant=A.RT_VARIANT_MEGAKERNEL)
+    b, sb, _ = gpu_render(sc, cam, variant=A.RT_VARIANT_HEADTAIL)
+    c, sc_, _ = gpu_render(sc, cam, variant=A.RT_VARIANT_HEADTAIL)
+    assert sa.rays == sb.rays == sc_.rays
+    assert np.array_equal(b, c)  # deterministic
+    assert np.allclose(a, b, rtol=2e-6, atol=1e-7)
+
+
 def test_wavefront_variant_parity_with_the_oracle(oracle):
     sc = BuiltinScene(10)
     cam = sc.camera(240, 135, 4, 50)

@@ -16,6 +16,13 @@ def run(**kw):
     _, _, st = r.readback(linear=False)
     return st.rays / (e0.elapsed_time(e1) / 2) / 1e6
 print("megakernel", f"{run(variant=1):.2f} Grays/s", flush=True)
+for threads in (0, 768, 640, 512):
+    try:
+        print("head/tail threads", threads, f"{run(variant=3, block_threads=threads):.2f} Grays/s", flush=True)
+    except Exception as e:
+        print("head/tail threads", threads, "failed:", str(e)[:120])
+if len(sys.argv) > 1 and sys.argv[1] == "ht":
+    sys.exit(0)
 for slots in (64, 96):
     for idle, leaf, refill in ((16, 16, 16), (16, 16, 8), (24, 16, 8), (12, 12, 6), (8, 16, 8)):
         fl = ((slots // 32) << 12) | (idle << 16) | (leaf << 21) | (refill << 26)
