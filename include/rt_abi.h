@@ -163,9 +163,10 @@ typedef struct rt_camera {
     double background[3];              /* constant colour (kernel.cu:77,197) */
 } rt_camera;
 
-/* Kernel variants (rt_render_params.variant).  Both render the same image bit for bit. */
+/* Kernel variants (rt_render_params.variant).  Megakernel and wavefront render the same image bit for
+ * bit; head/tail the same up to the fp32 order in which a pixel's paths are summed. */
 enum {
-    RT_VARIANT_AUTO = 0,       /* the megakernel: measured faster on every scene */
+    RT_VARIANT_AUTO = 0,       /* head/tail when the scene fits in shared memory, else megakernel */
     RT_VARIANT_MEGAKERNEL = 1, /* persistent-thread megakernel                                    */
     RT_VARIANT_WAVEFRONT = 2,  /* on-chip wavefront: extend / shade / gen over warp-local queues  */
     RT_VARIANT_HEADTAIL = 3    /* synchronous heads (new samples) + queued tails (continuations)   */
@@ -247,6 +248,7 @@ typedef struct rt_scene_info {
     int32_t n_prims_baked, n_nodes, n_media, max_depth_bvh;
     int32_t features;      /* RT_FEAT_* bitmask that selected the kernel instantiation */
     int32_t scene_in_smem; /* 1 when nodes+prims+materials are staged in shared memory */
+    int32_t variant;       /* RT_VARIANT_* the last rt_render ran (what AUTO resolved to)    */
     uint64_t device_bytes;
     int32_t medium_visits[8]; /* T2: reference-topology visit multiplicity per medium_id */
 } rt_scene_info;

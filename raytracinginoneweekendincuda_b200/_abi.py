@@ -99,7 +99,7 @@ class rt_stats(C.Structure):
 class rt_scene_info(C.Structure):
     _fields_ = [("n_prims_baked", C.c_int32), ("n_nodes", C.c_int32), ("n_media", C.c_int32),
                 ("max_depth_bvh", C.c_int32), ("features", C.c_int32), ("scene_in_smem", C.c_int32),
-                ("device_bytes", C.c_uint64), ("medium_visits", C.c_int32 * 8)]
+                ("variant", C.c_int32), ("device_bytes", C.c_uint64), ("medium_visits", C.c_int32 * 8)]
 
 
 # oracle/rt_oracle.cpp

@@ -1011,6 +1011,7 @@ struct rt_scene_s {
     rt_camera lastCam{};
     bool rendered = false;
     int pickedFeatures = 0;
+    int pickedVariant = 0;
 };
 
 extern "C" {
@@ -1148,8 +1149,20 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
         rt_set_error("rt_render: unknown variant %d", p->variant);
         return RT_ERR_INVALID;
     }
-    const bool wave = p->variant == RT_VARIANT_WAVEFRONT;
-    const bool headTail = p->variant == RT_VARIANT_HEADTAIL;
+    // AUTO: head/tail when the scene can stay in shared memory beside its queues (measured +18..32 % over the
+    // megakernel on scenes 0, 7, 8, 10); the megakernel when the scene is read through L1 (scene 9: the queues
+    // would take 75 KB from the L1 carve-out, measured -26 %) or the sample range exceeds the packed index.
+    int variant = p->variant;
+    if (variant == RT_VARIANT_AUTO) {
+        const int fc = h->dev.features == 0 ? 0 : 1;
+        const int levels = std::max(3, std::min(kMaxStackLevels, h->host->max_depth + 3));
+        const size_t need = (size_t)256 * 4 * levels + (size_t)(256 / 32) * HtWarpBytes(fc ? RT_FEAT_MOVING : 0) + 16 + h->stagedBytes;
+        const bool fits = !(p->flags & 0x200) && need <= (size_t)h->maxSmemOptin;
+        variant = (fits && (long long)p->sample_end - p->sample_begin <= RT_HT_MAX_SAMPLES) ? RT_VARIANT_HEADTAIL
+                                                                                            : RT_VARIANT_MEGAKERNEL;
+    }
+    const bool wave = variant == RT_VARIANT_WAVEFRONT;
+    const bool headTail = variant == RT_VARIANT_HEADTAIL;
     if (headTail && (long long)p->sample_end - p->sample_begin > RT_HT_MAX_SAMPLES) {
         rt_set_error("rt_render: the head/tail variant takes at most %d samples per call", RT_HT_MAX_SAMPLES);
         return RT_ERR_INVALID;
@@ -1256,7 +1269,8 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
                      h->maxSmemOptin);
         return RT_ERR_INVALID;
     }
-    KernelFn fn = PickKernelForFeatures(h->dev.features, p->variant, smem, wantStats, &h->pickedFeatures);
+    KernelFn fn = PickKernelForFeatures(h->dev.features, variant, smem, wantStats, &h->pickedFeatures);
+    h->pickedVariant = variant;
     RT_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     const int nTiles = a.tilesX * a.tilesY;
     const int warpsPerBlock = threads / 32;
@@ -1376,6 +1390,7 @@ int rt_scene_get_info(rt_scene_handle h, rt_scene_info* info)
     info->max_depth_bvh = h->host->max_depth;
     info->features = h->dev.features;
     info->scene_in_smem = h->fitsSmem ? 1 : 0;
+    info->variant = h->pickedVariant;
     info->device_bytes = h->deviceBytes;
     for (int k = 0; k < 8; ++k) info->medium_visits[k] = h->host->medium_visits[k];
     return RT_OK;

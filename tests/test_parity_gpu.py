@@ -82,13 +82,27 @@ def test_bvh_modes_agree(earth, sid):
     assert abs(int(sa.rays) - int(sb.rays)) <= 4 and abs(int(sa.rays) - int(sc_.rays)) <= 4
 
 
-def test_shared_memory_and_global_paths_are_bit_identical():
+@pytest.mark.parametrize("variant", [A.RT_VARIANT_MEGAKERNEL, A.RT_VARIANT_WAVEFRONT, A.RT_VARIANT_HEADTAIL])
+def test_shared_memory_and_global_paths_are_bit_identical(variant):
     sc = BuiltinScene(10)
     cam = sc.camera(160, 90, 4, 50)
-    a, sa, ia = gpu_render(sc, cam)
-    b, sb, ib = gpu_render(sc, cam, flags=0x200)
-    assert ia.scene_in_smem == 1 and ib.scene_in_smem == 0
+    a, sa, ia = gpu_render(sc, cam, variant=variant)
+    b, sb, ib = gpu_render(sc, cam, variant=variant, flags=A.RT_FLAG_SCENE_IN_GLOBAL)
+    assert ia.scene_in_smem == 1 and ib.scene_in_smem == 0 and ia.variant == ib.variant == variant
     assert np.array_equal(a, b) and sa.rays == sb.rays
+
+
+def test_auto_picks_headtail_for_shared_memory_scenes_and_megakernel_otherwise(earth):
+    """head/tail where the scene stays in shared memory beside the queues, the megakernel
+    where the scene is read through L1 (scene 9) or the sample range exceeds the packed sample index."""
+    sc = BuiltinScene(10)
+    _, _, info = gpu_render(sc, sc.camera(64, 36, 2, 50))
+    assert info.variant == A.RT_VARIANT_HEADTAIL and info.scene_in_smem == 1
+    sc9 = scene_for(9, earth)
+    _, _, info9 = gpu_render(sc9, sc9.camera(64, 36, 2, 50))
+    assert info9.variant == A.RT_VARIANT_MEGAKERNEL and info9.scene_in_smem == 0
+    _, _, info = gpu_render(sc, sc.camera(2, 2, 600000, 50))
+    assert info.variant == A.RT_VARIANT_MEGAKERNEL
 
 
 @pytest.mark.parametrize("sid,W,H,spp", [(10, 200, 113, 6), (0, 96, 54, 4), (7, 64, 64, 6), (8, 64, 64, 6), (9, 96, 54, 3)])

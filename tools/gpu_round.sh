@@ -14,5 +14,5 @@ CMD="python bench.py --steps 2 --warmup 3 --spp 32 --no-cpu-baseline --no-e2e"
 $CMD > $O/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_launches_$TAG.log 2>&1
 $CMD > $O/plain2_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k "regex:Render(Mega|Wave)" -s 3 -c 1 -f -o $O/prof_${TAG}_book1 $CMD > $O/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:Render(Mega|Wave|HeadTail)" -s 3 -c 1 -f -o $O/prof_${TAG}_book1 $CMD > $O/ncu_full_$TAG.log 2>&1
 tail -3 $O/ncu_full_$TAG.log
