@@ -433,7 +433,8 @@ def run_b200_arm():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_bytes = H * W * 3 * 4 * 2  # accumulator read-modify-write, once per pixel per launch
     roofline = {
-        "bound": "fp32", "kernel": "RenderMega", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": {1: "RenderMega", 2: "RenderWave", 3: "RenderHeadTail"}.get(info.variant, "?"),
+        "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
         "frac": achieved / peak.value if peak.value else None,
         "traffic": NCU_DRAM_BYTES_4K_LAUNCH if (W, H) == (3840, 2160) else None,
         "peak_source": "FFMA microbenchmark run live on this GPU (rt_measure_fp32_peak); MEASURED_PEAKS.json "

@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderHeadTail(const 
             {
                 const unsigned am = __ballot_sync(FULL, hasAdd);
                 int rank = 0;
-                if (hasAdd) rank = __popc(__match_any_sync(am, owner) & ltMask);
+                if (tailRound && hasAdd) rank = __popc(__match_any_sync(am, owner) & ltMask); // heads: owner == lane
                 for (int r = 0;; ++r) {
                     if (hasAdd && rank == r) {
                         SUM[owner] += add.x;

@@ -13,12 +13,12 @@ r = Renderer(sc.desc, max_leaf_prims=int(os.environ.get('LEAF', '0')))
 stream = torch.cuda.current_stream().cuda_stream
 for f in sys.argv[1:]:
     flags = int(f, 0)
-    r.render(cam, stream=stream, flags=flags)
+    r.render(cam, stream=stream, flags=flags, variant=int(os.environ.get("VARIANT", "0")))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3):
-        r.render(cam, stream=stream, flags=flags)
+        r.render(cam, stream=stream, flags=flags, variant=int(os.environ.get("VARIANT", "0")))
     e1.record()
     torch.cuda.synchronize()
     _, _, st = r.readback(linear=False)
