@@ -703,10 +703,13 @@ RT_DEV StreamKey MakeKey(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_
 // unless it is within rounding of the sphere.
 RT_DEV bool BallCandidate(uint32_t bx, uint32_t by, uint32_t bz, d3& p)
 {
-    const float x = rt_bits_to_u01(bx), y = rt_bits_to_u01(by), z = rt_bits_to_u01(bz);
-    const float fx = 2.0f * x - 1.0f, fy = 2.0f * y - 1.0f, fz = 2.0f * z - 1.0f;
+    // fp32 pre-test on 2u-1 formed in one FMA from the bits (within 1e-7 of the exact value: the band below
+    // is 1e-5); the exact FP64 candidate is built from the fp32 uniform only when the pre-test lets it through
+    const float k1 = 4.6566128730773926e-10f, k0 = 2.3283064365386963e-10f - 1.0f; // 2^-31, 2^-32 - 1
+    const float fx = fmaf((float)bx, k1, k0), fy = fmaf((float)by, k1, k0), fz = fmaf((float)bz, k1, k0);
     const float l2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
     if (l2 >= 1.00001f) return false;
+    const float x = rt_bits_to_u01(bx), y = rt_bits_to_u01(by), z = rt_bits_to_u01(bz);
     p = make_d3(fma(2.0, (double)x, -1.0), fma(2.0, (double)y, -1.0), fma(2.0, (double)z, -1.0));
     return !(l2 > 0.99999f && dot(p, p) >= 1.0);
 }
