@@ -166,7 +166,7 @@ typedef struct rt_camera {
 /* Kernel variants (rt_render_params.variant).  Megakernel and wavefront render the same image bit for
  * bit; head/tail the same up to the fp32 order in which a pixel's paths are summed. */
 enum {
-    RT_VARIANT_AUTO = 0,       /* head/tail when the scene fits in shared memory, else megakernel */
+    RT_VARIANT_AUTO = 0,       /* head/tail (megakernel beyond 2^19 samples per call)              */
     RT_VARIANT_MEGAKERNEL = 1, /* persistent-thread megakernel                                    */
     RT_VARIANT_WAVEFRONT = 2,  /* on-chip wavefront: extend / shade / gen over warp-local queues  */
     RT_VARIANT_HEADTAIL = 3    /* synchronous heads (new samples) + queued tails (continuations)   */

@@ -121,6 +121,9 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
 // resident warps hide (profiles/README.md).
 // The feature-complete instantiations need ~125 registers and stay at 512.
 constexpr int MegaMaxThreads(int feat) { return feat == 0 ? 768 : 512; }
+// The head/tail kernel holds no path state across rounds: its feature-complete instantiation fits 96
+// registers, i.e. 640 threads.
+constexpr int HtMaxThreads(int feat) { return feat == 0 ? 768 : 640; }
 
 template <int FEAT, bool SMEM, bool STATS>
 __global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderMega(const DevScene scene, const DevCamera cam, const RenderArgs args)
@@ -633,7 +636,7 @@ __host__ __device__ constexpr int HtWarpBytes(int feat)
 #define RT_HT_MAX_SAMPLES (1 << 19) /* sample index relative to sample_begin is packed in 19 bits */
 
 template <int FEAT, bool SMEM, bool STATS>
-__global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderHeadTail(const DevScene scene, const DevCamera cam, const RenderArgs args)
+__global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHeadTail(const DevScene scene, const DevCamera cam, const RenderArgs args)
 {
     extern __shared__ __align__(16) char smem[];
     const uint32_t smemBase = SmemAddr(smem);
@@ -1149,18 +1152,11 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
         rt_set_error("rt_render: unknown variant %d", p->variant);
         return RT_ERR_INVALID;
     }
-    // AUTO: head/tail when the scene can stay in shared memory beside its queues (measured +18..32 % over the
-    // megakernel on scenes 0, 7, 8, 10); the megakernel when the scene is read through L1 (scene 9: the queues
-    // would take 75 KB from the L1 carve-out, measured -26 %) or the sample range exceeds the packed index.
+    // AUTO: the head/tail kernel (measured +17..39 % over the megakernel on scenes 0, 7, 8, 9, 10) unless the
+    // sample range exceeds its packed sample index.
     int variant = p->variant;
-    if (variant == RT_VARIANT_AUTO) {
-        const int fc = h->dev.features == 0 ? 0 : 1;
-        const int levels = std::max(3, std::min(kMaxStackLevels, h->host->max_depth + 3));
-        const size_t need = (size_t)256 * 4 * levels + (size_t)(256 / 32) * HtWarpBytes(fc ? RT_FEAT_MOVING : 0) + 16 + h->stagedBytes;
-        const bool fits = !(p->flags & 0x200) && need <= (size_t)h->maxSmemOptin;
-        variant = (fits && (long long)p->sample_end - p->sample_begin <= RT_HT_MAX_SAMPLES) ? RT_VARIANT_HEADTAIL
-                                                                                            : RT_VARIANT_MEGAKERNEL;
-    }
+    if (variant == RT_VARIANT_AUTO)
+        variant = (long long)p->sample_end - p->sample_begin <= RT_HT_MAX_SAMPLES ? RT_VARIANT_HEADTAIL : RT_VARIANT_MEGAKERNEL;
     const bool wave = variant == RT_VARIANT_WAVEFRONT;
     const bool headTail = variant == RT_VARIANT_HEADTAIL;
     if (headTail && (long long)p->sample_end - p->sample_begin > RT_HT_MAX_SAMPLES) {
@@ -1227,7 +1223,7 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     a.mediaBytes = pad16(std::max<size_t>(1, pk.media.size()) * sizeof(DevMedium));
     a.materialsBytes = pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial));
 
-    const int maxThreads = wave ? 512 : MegaMaxThreads(h->dev.features == 0 ? 0 : 1);
+    const int maxThreads = wave ? 512 : (headTail ? HtMaxThreads(h->dev.features == 0 ? 0 : 1) : MegaMaxThreads(h->dev.features == 0 ? 0 : 1));
     int threads = p->block_threads > 0 ? p->block_threads : maxThreads;
     threads = std::max(32, std::min(maxThreads, (threads / 32) * 32));
     int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;
@@ -1240,12 +1236,14 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     const int featClass = h->dev.features == 0 ? kFeatSpheres : ((h->dev.features & ~kFeatMotion) == 0 ? kFeatMotion : kFeatAll);
     if (headTail && p->block_threads <= 0 && !(p->flags & 0x200)) {
         // the largest block whose stacks + queues still leave room for the scene in shared memory
-        for (int cand = maxThreads; cand >= 256; cand -= 128) {
-            threads = cand;
+        // (if none does, the scene stays in global memory and the block is as large as registers allow)
+        threads = maxThreads;
+        for (int cand = maxThreads; cand >= 384; cand -= 128)
             if ((size_t)cand * 4 * stackLevels + (size_t)(cand / 32) * HtWarpBytes(featClass) + 16 + h->stagedBytes <=
-                (size_t)h->maxSmemOptin)
+                (size_t)h->maxSmemOptin) {
+                threads = cand;
                 break;
-        }
+            }
     }
     const size_t stackBytes = (size_t)threads * 4 * stackLevels;
     size_t poolBytes = headTail ? (size_t)(threads / 32) * HtWarpBytes(featClass) + 16 : 0;

@@ -92,15 +92,15 @@ def test_shared_memory_and_global_paths_are_bit_identical(variant):
     assert np.array_equal(a, b) and sa.rays == sb.rays
 
 
-def test_auto_picks_headtail_for_shared_memory_scenes_and_megakernel_otherwise(earth):
-    """head/tail where the scene stays in shared memory beside the queues, the megakernel
-    where the scene is read through L1 (scene 9) or the sample range exceeds the packed sample index."""
+def test_auto_picks_headtail_and_falls_back_to_the_megakernel_for_huge_sample_ranges(earth):
+    """head/tail everywhere it applies (scene in shared memory or not); the megakernel when
+    the sample range exceeds the head/tail kernel's packed sample index."""
     sc = BuiltinScene(10)
     _, _, info = gpu_render(sc, sc.camera(64, 36, 2, 50))
     assert info.variant == A.RT_VARIANT_HEADTAIL and info.scene_in_smem == 1
     sc9 = scene_for(9, earth)
     _, _, info9 = gpu_render(sc9, sc9.camera(64, 36, 2, 50))
-    assert info9.variant == A.RT_VARIANT_MEGAKERNEL and info9.scene_in_smem == 0
+    assert info9.variant == A.RT_VARIANT_HEADTAIL and info9.scene_in_smem == 0
     _, _, info = gpu_render(sc, sc.camera(2, 2, 600000, 50))
     assert info.variant == A.RT_VARIANT_MEGAKERNEL
 
