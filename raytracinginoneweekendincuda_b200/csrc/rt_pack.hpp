@@ -227,7 +227,7 @@ struct Builder {
         double leafCost = 0.0;
         for (int id : ids) leafCost += IsectCost(items[id].type);
 
-        const int kBins = 16;
+        const int kBins = 64;
         double bestCost = DBL_MAX;
         int bestAxis = -1, bestBin = -1;
         const double invArea = box.Area() > 0 ? 1.0 / box.Area() : 0.0;

@@ -23,4 +23,5 @@ for f in sys.argv[1:]:
     torch.cuda.synchronize()
     _, _, st = r.readback(linear=False)
     ms = e0.elapsed_time(e1) / 3
-    print(f"scene {sid} flags {f}: {ms:.2f} ms {st.rays / ms / 1e6:.2f} Grays/s", flush=True)
+    extra = f" node/ray {st.node_tests / st.rays:.2f} prim/ray {st.prim_tests / st.rays:.3f}" if flags & 0x100 else ""
+    print(f"scene {sid} flags {f}: {ms:.2f} ms {st.rays / ms / 1e6:.2f} Grays/s" + extra, flush=True)
