@@ -213,6 +213,32 @@ def test_config2_full_size_4k_properties(oracle):
     assert rmse < 0.1, rmse
 
 
+@pytest.mark.parametrize("sid,W,H,spp,div", [(0, 1920, 1080, 4, 8), (8, 1024, 1024, 4, 8), (9, 3840, 2160, 2, 16)])
+def test_configs_3_to_5_full_size_properties(oracle, earth, sid, W, H, spp, div):
+    """BASELINE.json configs[2..4] at their full image sizes (spp cut so that each runs in seconds):
+    the sample split of the multi-GPU path adds up ray for ray, and rays per path and mean radiance agree
+    with the FP64 oracle rendered at 1/div size (same camera, same statistics)."""
+    sc = scene_for(sid, earth)
+    cam = sc.camera(W, H, spp, 50)
+    r = Renderer(sc.desc)
+    r.render(cam, 0, spp)
+    full, _, sf = r.readback()
+    for k in range(spp):
+        r.render(cam, k, k + 1, clear=(k == 0))
+    parts, _, sp = r.readback()
+    r.close()
+    assert sp.rays == sf.rays
+    assert np.allclose(parts, full, rtol=1e-5, atol=1e-6)
+    assert np.isfinite(full).all() and full.min() >= 0.0
+    cam_s = sc.camera(W // div, H // div, spp, 50)
+    want, ost = oracle_render(oracle, sc, cam_s, 0, spp)
+    rpp_gpu, rpp_or = sf.rays / (W * H * spp), ost.rays / ost.paths
+    assert abs(rpp_gpu - rpp_or) < 0.02 * rpp_or, (rpp_gpu, rpp_or)
+    m_gpu = full.mean(axis=(0, 1), dtype=np.float64)
+    m_or = (want / spp).mean(axis=(0, 1))
+    assert np.allclose(m_gpu, m_or, rtol=0.05), (m_gpu, m_or)
+
+
 def _ref_gpu(args, env=None, cwd=None):
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu")
     if not os.path.exists(exe):
