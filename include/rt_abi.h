@@ -243,6 +243,10 @@ int rt_readback(rt_scene_handle scene, const float* accum, float* linear_rgb, ui
 
 int rt_scene_free(rt_scene_handle scene);
 
+/* Scene arenas and frame-sized buffers of freed handles are kept (up to 8 blocks per process) and reused by
+ * the next upload / render of the same size; this returns them to the driver. */
+int rt_release_cached_memory(void);
+
 /* Scene summary after upload (prim/node counts, bytes, kernel class). */
 typedef struct rt_scene_info {
     int32_t n_prims_baked, n_nodes, n_media, max_depth_bvh;

@@ -164,6 +164,8 @@ def declare_device(lib: C.CDLL) -> None:
                                         C.c_int32, C.c_void_p, C.c_int32]
     lib.rt_measure_fp32_peak.restype = C.c_int
     lib.rt_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.rt_release_cached_memory.restype = C.c_int
+    lib.rt_release_cached_memory.argtypes = []
     lib.rt_abi_sizeof.restype = C.c_int
     lib.rt_abi_sizeof.argtypes = [C.c_char_p]
 

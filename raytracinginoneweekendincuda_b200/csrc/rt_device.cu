@@ -1375,6 +1375,19 @@ int rt_scene_free(rt_scene_handle h)
     return RT_OK;
 }
 
+int rt_release_cached_memory(void)
+{
+    std::vector<BigBlock> blocks;
+    {
+        std::lock_guard<std::mutex> lock(gBigMutex);
+        blocks.swap(gBigCache);
+    }
+    for (const BigBlock& b : blocks) {
+        if (cudaSetDevice(b.device) == cudaSuccess) cudaFree(b.ptr);
+    }
+    return RT_OK;
+}
+
 int rt_scene_get_info(rt_scene_handle h, rt_scene_info* info)
 {
     if (!h || !info) {

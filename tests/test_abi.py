@@ -66,6 +66,10 @@ def test_malformed_scenes_are_rejected(lib):
     assert lib.rt_scene_upload(None, C.byref(opt), C.byref(h)) == A.RT_ERR_INVALID
 
 
+def test_release_cached_memory_is_callable_without_a_device(lib):
+    assert lib.rt_release_cached_memory() == A.RT_OK
+
+
 def test_unknown_scene_id_is_an_error(lib):
     h = C.c_void_p()
     assert lib.rt_host_scene_builtin(77, None, 0, 0, C.byref(h)) == A.RT_ERR_INVALID
