@@ -121,9 +121,9 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
 // resident warps hide (profiles/README.md).
 // The feature-complete instantiations need ~125 registers and stay at 512.
 constexpr int MegaMaxThreads(int feat) { return feat == 0 ? 768 : 512; }
-// The head/tail kernel holds no path state across rounds: its feature-complete instantiation fits 96
-// registers, i.e. 640 threads.
-constexpr int HtMaxThreads(int feat) { return feat == 0 ? 768 : 640; }
+// The head/tail kernel holds no path state across rounds: with moving spheres and checker textures it
+// still fits 80 registers (768 threads); the feature-complete instantiation runs at 640.
+constexpr int HtMaxThreads(int feat) { return (feat & ~(RT_FEAT_MOVING | RT_FEAT_TEXTURE)) == 0 ? 768 : 640; }
 
 template <int FEAT, bool SMEM, bool STATS>
 __global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderMega(const DevScene scene, const DevCamera cam, const RenderArgs args)
@@ -910,7 +910,7 @@ template <int FEAT> KernelFn PickKernel(int variant, bool smem, bool stats)
 // Instantiations: spheres only / + moving spheres and textures / everything.
 constexpr int kFeatSpheres = 0;
 constexpr int kFeatMotion = RT_FEAT_MOVING | RT_FEAT_TEXTURE;
-constexpr int kFeatAll = RT_FEAT_MOVING | RT_FEAT_QUAD | RT_FEAT_MEDIUM | RT_FEAT_TEXTURE;
+constexpr int kFeatAll = RT_FEAT_MOVING | RT_FEAT_QUAD | RT_FEAT_MEDIUM | RT_FEAT_TEXTURE | RT_FEAT_TEXTURE_HEAVY;
 
 KernelFn PickKernelForFeatures(int features, int variant, bool smem, bool stats, int* picked)
 {
@@ -1223,7 +1223,8 @@ int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p
     a.mediaBytes = pad16(std::max<size_t>(1, pk.media.size()) * sizeof(DevMedium));
     a.materialsBytes = pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial));
 
-    const int maxThreads = wave ? 512 : (headTail ? HtMaxThreads(h->dev.features == 0 ? 0 : 1) : MegaMaxThreads(h->dev.features == 0 ? 0 : 1));
+    const int featClassEarly = h->dev.features == 0 ? 0 : ((h->dev.features & ~(RT_FEAT_MOVING | RT_FEAT_TEXTURE)) == 0 ? (RT_FEAT_MOVING | RT_FEAT_TEXTURE) : 31);
+    const int maxThreads = wave ? 512 : (headTail ? HtMaxThreads(featClassEarly) : MegaMaxThreads(h->dev.features == 0 ? 0 : 1));
     int threads = p->block_threads > 0 ? p->block_threads : maxThreads;
     threads = std::max(32, std::min(maxThreads, (threads / 32) * 32));
     int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;

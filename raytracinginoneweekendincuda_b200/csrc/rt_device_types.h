@@ -136,7 +136,8 @@ struct DevImage {
 #define RT_FEAT_MOVING 1
 #define RT_FEAT_QUAD 2
 #define RT_FEAT_MEDIUM 4
-#define RT_FEAT_TEXTURE 8 /* any non-solid texture */
+#define RT_FEAT_TEXTURE 8        /* any non-solid texture */
+#define RT_FEAT_TEXTURE_HEAVY 16 /* image or Perlin-noise textures (their code costs ~25 registers) */
 
 struct DevScene {
     const DevNode* nodes;

@@ -539,6 +539,9 @@ struct Packer {
                 } else {
                     x.texture = m.texture;
                     out.features |= RT_FEAT_TEXTURE;
+                    for (int k = 0; k < d.n_textures; ++k) // a checker may lead to any texture of the scene
+                        if (d.textures[k].type == RT_TEX_IMAGE || d.textures[k].type == RT_TEX_NOISE)
+                            out.features |= RT_FEAT_TEXTURE_HEAVY;
                 }
             }
             out.materials.push_back(x);

@@ -638,7 +638,7 @@ RT_DEV void SphereUV(f3 p, float& u, float& v)
 }
 
 // Texture.h:29-176
-template <bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv, int tex, const Hit& h, bool sphereLike)
+template <int FEAT, bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv, int tex, const Hit& h, bool sphereLike)
 {
     for (int guard = 0; guard < 16; ++guard) {
         const DevTexture* t = &sv.textures[tex];
@@ -651,6 +651,7 @@ template <bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv, int tex, 
             tex = ((xi + yi + zi) % 2 == 0) ? __ldg(&t->even) : __ldg(&t->odd);
             continue;
         }
+        if (!(FEAT & RT_FEAT_TEXTURE_HEAVY)) return make_f3(0.0f, 0.0f, 0.0f); // no image / noise texture in this scene
         if (type == RT_TEX_IMAGE) {
             // Texture.h:110-133: nearest texel, v flipped, cyan when there is no image
             const int idx = __ldg(&t->index);
@@ -748,7 +749,7 @@ RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, const d3& dirIn, do
     emitted = make_f3(0.0f, 0.0f, 0.0f);
     f3 colour = make_f3(m0.x, m0.y, m0.z);
     if ((FEAT & RT_FEAT_TEXTURE) && tex >= 0 && type != RT_MAT_METAL && type != RT_MAT_DIELECTRIC)
-        colour = TextureValue<SMEM>(sv, tex, h, sphereLike);
+        colour = TextureValue<FEAT, SMEM>(sv, tex, h, sphereLike);
     if (type == RT_MAT_LAMBERTIAN) { // Material.h:68-86
         dir = h.n + RandomInUnitSphere(rng);
         if (fabs(dir.x) < 1e-8 && fabs(dir.y) < 1e-8 && fabs(dir.z) < 1e-8) dir = h.n;
