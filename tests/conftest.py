@@ -30,7 +30,8 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def built():
     """Make sure the in-tree libraries exist (compiles them when a toolchain is here)."""
-    if not (os.path.exists(_build.lib_path()) and os.path.exists(_build.oracle_path())):
+    cli = os.path.join(ROOT, "raytracinginoneweekendincuda_b200", "rt_cli")
+    if not (os.path.exists(_build.lib_path()) and os.path.exists(_build.oracle_path()) and os.path.exists(cli)):
         _build.build_product()
         _build.build_oracle()
     return True
