@@ -358,7 +358,7 @@ def test_readback_srgb_and_ppm(tmp_path):
     assert len(lines) == 3 + 40 * 20 + 1
 
 
-def test_cli_writes_the_same_ppm_as_the_api(tmp_path):
+def test_cli_writes_the_same_ppm_as_the_api(built, tmp_path):
     """rt_cli = the reference's main() (kernel.cu:570-742) with flags, over the same C ABI."""
     cli = os.path.join(ROOT, "raytracinginoneweekendincuda_b200", "rt_cli")
     out = tmp_path / "cli.ppm"
