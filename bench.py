@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0)
+    ap.add_argument("--upload-flags", type=lambda x: int(x, 0), default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -311,7 +312,7 @@ def run_b200_arm():
     kw = dict(seed=SEED, stream=stream, accum_ptr=accum.data_ptr(), block_threads=ARGS.block_threads,
               blocks_per_sm=ARGS.blocks_per_sm, variant=ARGS.variant, flags=ARGS.flags)
 
-    r = Renderer(sc.desc, device=local)
+    r = Renderer(sc.desc, device=local, upload_flags=ARGS.upload_flags)
     info_desc_bytes = sc.desc_bytes()
 
     def step_resident(time_kernel=None):
@@ -369,7 +370,7 @@ def run_b200_arm():
         def step_e2e():
             t = [time.perf_counter()]
             flush.zero_()
-            rr = Renderer(sc.desc, device=local)  # deep copy + bake + BVH + H2D of every table
+            rr = Renderer(sc.desc, device=local, upload_flags=ARGS.upload_flags)  # deep copy + bake + BVH + H2D of every table
             t.append(time.perf_counter())
             rr.render(cam, s0, s1, clear=True, **kw)
             if trace:
@@ -433,7 +434,7 @@ def run_b200_arm():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_bytes = H * W * 3 * 4 * 2  # accumulator read-modify-write, once per pixel per launch
     roofline = {
-        "bound": "fp32", "kernel": {1: "RenderMega", 2: "RenderWave", 3: "RenderHeadTail"}.get(info.variant, "?"),
+        "bound": "fp32", "kernel": {1: "RenderMega", 2: "RenderWave", 3: "RenderHeadTail", 4: "RenderHitQueue"}.get(info.variant, "?"),
         "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
         "frac": achieved / peak.value if peak.value else None,
         "traffic": NCU_DRAM_BYTES_4K_LAUNCH if (W, H) == (3840, 2160) else None,

@@ -164,12 +164,14 @@ typedef struct rt_camera {
 } rt_camera;
 
 /* Kernel variants (rt_render_params.variant).  Megakernel and wavefront render the same image bit for
- * bit; head/tail the same up to the fp32 order in which a pixel's paths are summed. */
+ * bit; head/tail and hit-queue the same up to the fp32 order in which a pixel's paths are summed (hit-queue
+ * also refines hit points from a different starting value: equal to ~1e-14 relative). */
 enum {
-    RT_VARIANT_AUTO = 0,       /* head/tail (megakernel beyond 2^19 samples per call)              */
+    RT_VARIANT_AUTO = 0,       /* hit-queue (megakernel beyond 2^19 samples per call)              */
     RT_VARIANT_MEGAKERNEL = 1, /* persistent-thread megakernel                                    */
     RT_VARIANT_WAVEFRONT = 2,  /* on-chip wavefront: extend / shade / gen over warp-local queues  */
-    RT_VARIANT_HEADTAIL = 3    /* synchronous heads (new samples) + queued tails (continuations)   */
+    RT_VARIANT_HEADTAIL = 3,   /* synchronous heads (new samples) + queued continuation rays       */
+    RT_VARIANT_HITQUEUE = 4    /* synchronous heads + queued hits: shading runs on full warps      */
 };
 
 /* BVH the device traverses (rt_render_params.bvh / rt_upload_options.bvh). */
@@ -183,8 +185,12 @@ typedef struct rt_upload_options {
     int32_t device; /* CUDA device ordinal */
     int32_t bvh;    /* RT_BVH_* */
     int32_t max_leaf_prims; /* 0 = default */
-    int32_t _pad;
+    int32_t flags;  /* RT_UPLOAD_* */
 } rt_upload_options;
+
+enum {
+    RT_UPLOAD_NO_HOIST = 1 /* keep scene-sized primitives / media inside the BVH (A/B test of the hoisting) */
+};
 
 typedef struct rt_render_params {
     int32_t sample_begin, sample_end; /* global sample indices rendered by this call:
@@ -257,6 +263,18 @@ typedef struct rt_scene_info {
     int32_t medium_visits[8]; /* T2: reference-topology visit multiplicity per medium_id */
 } rt_scene_info;
 int rt_scene_get_info(rt_scene_handle scene, rt_scene_info* info);
+
+/* Host only (no CUDA call): what rt_scene_upload would build for this scene -- baking, BVH, hoisting, packing --
+ * as counts.  Lets hosts and CPU-only tests inspect the packer. */
+typedef struct rt_pack_info {
+    int32_t n_nodes, n_spheres, n_moving, n_quads, n_media, n_materials, n_mat_params;
+    int32_t max_depth_bvh; /* levels the traversal stack must hold (joins of mixed leaves included) */
+    int32_t features;      /* RT_FEAT_* */
+    int32_t n_hoisted;     /* scene-sized items tested before the tree (see RT_UPLOAD_NO_HOIST) */
+    uint32_t hoisted[4];   /* their leaf refs: type in bits 30..29 (0 sphere, 1 moving, 2 quad, 3 medium) */
+    uint64_t staged_bytes; /* nodes + primitives + materials: what a CTA stages in shared memory when it fits */
+} rt_pack_info;
+int rt_scene_pack_info(const rt_scene_desc* scene, const rt_upload_options* opt, rt_pack_info* out);
 
 const char* rt_last_error(void);
 

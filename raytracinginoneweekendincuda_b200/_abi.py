@@ -21,10 +21,11 @@ RT_XFORM_TRANSLATE, RT_XFORM_ROTATE_Y = 0, 1
 RT_OBJ_PRIM, RT_OBJ_LIST, RT_OBJ_MEDIUM = 0, 1, 2
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = 0, 1, 2, 3, 4
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_IMAGE, RT_TEX_NOISE = 0, 1, 2, 3
-RT_VARIANT_AUTO, RT_VARIANT_MEGAKERNEL, RT_VARIANT_WAVEFRONT, RT_VARIANT_HEADTAIL = 0, 1, 2, 3
+RT_VARIANT_AUTO, RT_VARIANT_MEGAKERNEL, RT_VARIANT_WAVEFRONT, RT_VARIANT_HEADTAIL, RT_VARIANT_HITQUEUE = 0, 1, 2, 3, 4
 RT_BVH_SAH, RT_BVH_REFERENCE, RT_BVH_NONE = 0, 1, 2
 RT_FLAG_STATS = 0x100
 RT_FLAG_SCENE_IN_GLOBAL = 0x200
+RT_UPLOAD_NO_HOIST = 1
 
 D3 = C.c_double * 3
 
@@ -81,7 +82,7 @@ class rt_camera(C.Structure):
 
 
 class rt_upload_options(C.Structure):
-    _fields_ = [("device", C.c_int32), ("bvh", C.c_int32), ("max_leaf_prims", C.c_int32), ("_pad", C.c_int32)]
+    _fields_ = [("device", C.c_int32), ("bvh", C.c_int32), ("max_leaf_prims", C.c_int32), ("flags", C.c_int32)]
 
 
 class rt_render_params(C.Structure):
@@ -100,6 +101,13 @@ class rt_scene_info(C.Structure):
     _fields_ = [("n_prims_baked", C.c_int32), ("n_nodes", C.c_int32), ("n_media", C.c_int32),
                 ("max_depth_bvh", C.c_int32), ("features", C.c_int32), ("scene_in_smem", C.c_int32),
                 ("variant", C.c_int32), ("device_bytes", C.c_uint64), ("medium_visits", C.c_int32 * 8)]
+
+
+class rt_pack_info(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("n_spheres", C.c_int32), ("n_moving", C.c_int32), ("n_quads", C.c_int32),
+                ("n_media", C.c_int32), ("n_materials", C.c_int32), ("n_mat_params", C.c_int32),
+                ("max_depth_bvh", C.c_int32), ("features", C.c_int32), ("n_hoisted", C.c_int32),
+                ("hoisted", C.c_uint32 * 4), ("staged_bytes", C.c_uint64)]
 
 
 # oracle/rt_oracle.cpp
@@ -133,6 +141,8 @@ def declare_host(lib: C.CDLL) -> None:
     lib.rt_host_scene_reference_bvh_nodes.argtypes = [C.c_void_p]
     lib.rt_host_scene_free.restype = C.c_int
     lib.rt_host_scene_free.argtypes = [C.c_void_p]
+    lib.rt_scene_pack_info.restype = C.c_int
+    lib.rt_scene_pack_info.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_upload_options), C.POINTER(rt_pack_info)]
     lib.rt_image_linearize_rgb8.restype = None
     lib.rt_image_linearize_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
 

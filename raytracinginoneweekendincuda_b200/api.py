@@ -104,9 +104,10 @@ class BuiltinScene:
 class Renderer:
     """A scene resident on one GPU: rt_scene_upload .. rt_scene_free."""
 
-    def __init__(self, desc, device: int = 0, bvh: int = A.RT_BVH_SAH, max_leaf_prims: int = 0):
+    def __init__(self, desc, device: int = 0, bvh: int = A.RT_BVH_SAH, max_leaf_prims: int = 0,
+                 upload_flags: int = 0):
         self.lib = load_library()
-        opt = A.rt_upload_options(device=device, bvh=bvh, max_leaf_prims=max_leaf_prims)
+        opt = A.rt_upload_options(device=device, bvh=bvh, max_leaf_prims=max_leaf_prims, flags=upload_flags)
         self._h = C.c_void_p()
         _check(self.lib, self.lib.rt_scene_upload(desc, C.byref(opt), C.byref(self._h)), "rt_scene_upload")
         self.device = device

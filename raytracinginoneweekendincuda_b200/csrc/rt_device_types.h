@@ -49,6 +49,7 @@ struct RT_ALIGN(16) DevNode {
 #define RT_REF_MAKE_LEAF(type, first, count) \
     (RT_REF_LEAF | ((uint32_t)(type) << 29) | (((uint32_t)(count)-1u) << 19) | (uint32_t)(first))
 #define RT_MAX_LEAF_PRIMS 1024
+#define RT_MAX_HOISTED 4 /* leaf refs tested before the tree is entered (rt_pack.hpp: hoisting) */
 #define RT_MAX_PRIMS_PER_TYPE (1 << 19)
 
 // Hit identifier carried out of traversal: type in bits 30..29, index below.
@@ -98,14 +99,20 @@ struct RT_ALIGN(16) DevMedium {
     double _p;
 };
 
-// ---- Material: 32 bytes.
+// ---- Material: 16 bytes = one 128-bit load.  Book 1 has one material per sphere (486 of them), and the table is
+// staged in shared memory next to the BVH: at 32 bytes it was a quarter of the staged scene.  The FP64 parameter of
+// the two materials that have one (metal fuzz, dielectric index: they enter the scattered direction, which is FP64
+// end to end) lives in a side table indexed by `index`.
+//   tt = type (RT_MAT_*, bits 0-2) | index << 3
+//   index: lambertian / light / isotropic -> texture + 1 (0 = the solid colour in r,g,b)
+//          metal / dielectric            -> slot in DevScene.mat_params
 struct RT_ALIGN(16) DevMaterial {
-    float r, g, b; // metal albedo, or the colour when `texture` < 0 (solid folded in)
-    float param;   // metal fuzz | dielectric index of refraction (fp32 copy)
-    int32_t type;  // RT_MAT_*
-    int32_t texture;
-    double param_d; // the same in FP64: it enters the scattered direction
+    float r, g, b; // metal albedo, or the colour when the texture is solid (folded in)
+    uint32_t tt;
 };
+#define RT_MAT_TT(type, index) ((uint32_t)(type) | ((uint32_t)(index) << 3))
+#define RT_MAT_TT_TYPE(tt) ((int)((tt)&7u))
+#define RT_MAT_TT_INDEX(tt) ((tt) >> 3)
 
 // ---- Texture: 48 bytes.
 struct RT_ALIGN(16) DevTexture {
@@ -147,10 +154,13 @@ struct DevScene {
     const DevQuad* quads;
     const DevMedium* media;
     const DevMaterial* materials;
+    const double* mat_params; // metal fuzz / dielectric index of refraction, FP64
     const DevTexture* textures;
     const DevPerlin* perlins;
     const DevImage* images;
     uint32_t root_ref;
+    uint32_t hoisted[RT_MAX_HOISTED];
+    int32_t n_hoisted;
     int32_t n_nodes, n_spheres, n_moving, n_quads, n_media, n_materials, n_textures;
     int32_t features;
 };

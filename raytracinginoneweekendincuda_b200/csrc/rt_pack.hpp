@@ -82,11 +82,14 @@ struct Packed {
     std::vector<DevQuad> quads;
     std::vector<DevMedium> media;
     std::vector<DevMaterial> materials;
+    std::vector<double> mat_params;
     std::vector<DevTexture> textures;
     std::vector<DevPerlin> perlins;
     std::vector<std::vector<uint8_t>> image_bytes;
     std::vector<int32_t> image_w, image_h;
     uint32_t root_ref = 0;
+    uint32_t hoisted[RT_MAX_HOISTED] = {0, 0, 0, 0}; // leaf refs tested before the tree is entered
+    int n_hoisted = 0;
     int features = 0;
     int max_depth = 0;
     int medium_visits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -175,7 +178,7 @@ struct Builder {
         }
     }
 
-    int NewLeaf(const std::vector<int>& ids, const Box3& box)
+    int NewLeaf(const std::vector<int>& ids, const Box3& box, int depth = 0)
     {
         // a leaf holds one primitive type, and a medium is always a leaf of its
         // own; mixed sets are chained through internal nodes sharing `box`
@@ -207,10 +210,12 @@ struct Builder {
                 made = (int)nodes.size() - 1;
             }
         }
+        // a mixed leaf is a chain of joins: each one is a level the traversal stack must hold
+        maxDepth = std::max(maxDepth, depth + (int)groups.size() - 1);
         return made;
     }
 
-    // Binned SAH, 16 bins, all three axes.
+    // Binned SAH, kBins bins, all three axes.
     int BuildSah(std::vector<int>& ids, int depth)
     {
         maxDepth = std::max(maxDepth, depth);
@@ -222,7 +227,7 @@ struct Builder {
             cbox.Grow(c);
         }
         const int n = (int)ids.size();
-        if (n == 1) return NewLeaf(ids, box);
+        if (n == 1) return NewLeaf(ids, box, depth);
 
         double leafCost = 0.0;
         for (int id : ids) leafCost += IsectCost(items[id].type);
@@ -275,7 +280,7 @@ struct Builder {
             }
         }
         const bool depthLeft = depth + (int)std::ceil(std::log2((double)std::max(n, 2))) < 26;
-        if (n <= maxLeaf && (bestAxis < 0 || leafCost <= bestCost)) return NewLeaf(ids, box);
+        if (n <= maxLeaf && (bestAxis < 0 || leafCost <= bestCost)) return NewLeaf(ids, box, depth);
 
         std::vector<int> L, R;
         if (bestAxis >= 0 && depthLeft) {
@@ -324,15 +329,15 @@ struct Builder {
         if (span == 1) {
             visits[order[start]] += 2;
             std::vector<int> one(1, order[start]);
-            return NewLeaf(one, box);
+            return NewLeaf(one, box, depth);
         }
         int l, r;
         if (span == 2) {
             visits[order[start]] += 1;
             visits[order[start + 1]] += 1;
             std::vector<int> a(1, order[start]), b(1, order[start + 1]);
-            l = NewLeaf(a, items[order[start]].box);
-            r = NewLeaf(b, items[order[start + 1]].box);
+            l = NewLeaf(a, items[order[start]].box, depth + 1);
+            r = NewLeaf(b, items[order[start + 1]].box, depth + 1);
         } else {
             for (int i = start + 1; i < end; ++i) {
                 const int key = order[i];
@@ -518,26 +523,24 @@ struct Packer {
             const rt_material& m = d.materials[i];
             DevMaterial x;
             std::memset(&x, 0, sizeof x);
-            x.type = m.type;
-            x.texture = -1;
-            if (m.type == RT_MAT_METAL) {
-                x.r = (float)m.albedo[0];
-                x.g = (float)m.albedo[1];
-                x.b = (float)m.albedo[2];
-                x.param = (float)m.fuzz;
-                x.param_d = m.fuzz;
-            } else if (m.type == RT_MAT_DIELECTRIC) {
-                x.param = (float)m.ior;
-                x.param_d = m.ior;
+            if (m.type == RT_MAT_METAL || m.type == RT_MAT_DIELECTRIC) {
+                if (m.type == RT_MAT_METAL) {
+                    x.r = (float)m.albedo[0];
+                    x.g = (float)m.albedo[1];
+                    x.b = (float)m.albedo[2];
+                }
+                x.tt = RT_MAT_TT(m.type, out.mat_params.size());
+                out.mat_params.push_back(m.type == RT_MAT_METAL ? m.fuzz : m.ior);
             } else {
                 if (m.texture < 0 || m.texture >= d.n_textures) throw std::invalid_argument("material texture out of range");
                 const rt_texture& t = d.textures[m.texture];
+                x.tt = RT_MAT_TT(m.type, 0);
                 if (t.type == RT_TEX_SOLID) {
                     x.r = (float)t.color[0];
                     x.g = (float)t.color[1];
                     x.b = (float)t.color[2];
                 } else {
-                    x.texture = m.texture;
+                    x.tt = RT_MAT_TT(m.type, m.texture + 1);
                     out.features |= RT_FEAT_TEXTURE;
                     for (int k = 0; k < d.n_textures; ++k) // a checker may lead to any texture of the scene
                         if (d.textures[k].type == RT_TEX_IMAGE || d.textures[k].type == RT_TEX_NOISE)
@@ -573,8 +576,26 @@ struct Packer {
     {
         if (d.abi_version != RT_ABI_VERSION) throw std::invalid_argument("rt_scene_desc.abi_version mismatch");
         if (d.n_objects <= 0 || d.n_prims <= 0) throw std::invalid_argument("empty scene");
+        if (d.n_xforms < 0 || d.n_materials < 0 || d.n_textures < 0 || d.n_perlins < 0 || d.n_images < 0)
+            throw std::invalid_argument("negative table size");
+        if (!d.objects || !d.prims || (d.n_xforms > 0 && !d.xforms) || (d.n_materials > 0 && !d.materials) ||
+            (d.n_textures > 0 && !d.textures) || (d.n_perlins > 0 && !d.perlins) || (d.n_images > 0 && !d.images))
+            throw std::invalid_argument("NULL table with a non-zero count");
+        for (int i = 0; i < d.n_objects; ++i)
+            if (d.objects[i].kind < RT_OBJ_PRIM || d.objects[i].kind > RT_OBJ_MEDIUM)
+                throw std::invalid_argument("unknown object kind");
+        for (int i = 0; i < d.n_xforms; ++i)
+            if (d.xforms[i].type != RT_XFORM_TRANSLATE && d.xforms[i].type != RT_XFORM_ROTATE_Y)
+                throw std::invalid_argument("unknown instance transform type");
+        for (int i = 0; i < d.n_materials; ++i)
+            if (d.materials[i].type < RT_MAT_LAMBERTIAN || d.materials[i].type > RT_MAT_ISOTROPIC)
+                throw std::invalid_argument("unknown material type");
+        for (int i = 0; i < d.n_textures; ++i)
+            if (d.textures[i].type < RT_TEX_SOLID || d.textures[i].type > RT_TEX_NOISE)
+                throw std::invalid_argument("unknown texture type");
         for (int i = 0; i < d.n_prims; ++i) {
             const rt_prim& p = d.prims[i];
+            if (p.type < RT_PRIM_SPHERE || p.type > RT_PRIM_QUAD) throw std::invalid_argument("unknown primitive type");
             if (p.material < 0 || p.material >= d.n_materials) throw std::invalid_argument("prim material out of range");
             if (p.xform_count < 0 || p.first_xform < 0 || p.first_xform + p.xform_count > d.n_xforms)
                 throw std::invalid_argument("prim xform chain out of range");
@@ -709,6 +730,38 @@ struct Packer {
             }
         }
         if (b.items.empty()) throw std::invalid_argument("scene has no primitives");
+
+        // Hoisting (SAH mode): an item whose box is most of the scene's box -- Book 1's ground sphere, scene 9's
+        // r = 5000 mist -- gains nothing from a hierarchy: nearly every ray enters its box, so its test would run
+        // inside the divergent leaf path of traversal.  Such items are taken out of the tree and tested up front by
+        // every lane of the warp together; the distance they return then culls the walk through the rest.  The
+        // closest hit is a minimum over all primitives (and medium draws are keyed), so the result does not change.
+        std::vector<int> hoistedItems;
+        if (opt.bvh == RT_BVH_SAH && !(opt.flags & RT_UPLOAD_NO_HOIST) && b.items.size() > 2) {
+            Box3 sceneBox;
+            for (const Item& it : b.items) sceneBox.Grow(it.box);
+            const double sceneArea = sceneBox.Area();
+            std::vector<Item> kept;
+            std::vector<std::vector<int>> keptRuns;
+            for (size_t k = 0; k < b.items.size(); ++k) {
+                const bool big = sceneArea > 0.0 && b.items[k].box.Area() >= 0.5 * sceneArea;
+                if (big && (int)hoistedItems.size() < RT_MAX_HOISTED && b.items.size() - hoistedItems.size() > 2) {
+                    hoistedItems.push_back((int)k);
+                } else {
+                    kept.push_back(b.items[k]);
+                    keptRuns.push_back(runOfItem[k]);
+                }
+            }
+            for (int k : hoistedItems) {
+                const Item& it = b.items[k];
+                out.hoisted[out.n_hoisted++] = it.type == RT_LEAF_MEDIUM ? RT_REF_MAKE_LEAF(RT_LEAF_MEDIUM, it.index, 1)
+                                                                         : EmitRun(it.type, runOfItem[k]);
+            }
+            if (!hoistedItems.empty()) {
+                b.items.swap(kept);
+                runOfItem.swap(keptRuns);
+            }
+        }
 
         int root;
         if (opt.bvh == RT_BVH_NONE) {

@@ -129,6 +129,15 @@ template <> RT_DEV double2 LdD2<true>(Base<true> b, uint32_t off)
 }
 template <> RT_DEV double2 LdD2<false>(Base<false> b, uint32_t off) { return __ldg(reinterpret_cast<const double2*>(b.a + off)); }
 
+template <bool SMEM> RT_DEV double LdD(Base<SMEM> b, uint32_t off);
+template <> RT_DEV double LdD<true>(Base<true> b, uint32_t off)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(b.a + off));
+    return v;
+}
+template <> RT_DEV double LdD<false>(Base<false> b, uint32_t off) { return __ldg(reinterpret_cast<const double*>(b.a + off)); }
+
 template <bool SMEM> RT_DEV int32_t LdI(Base<SMEM> b, uint32_t off);
 template <> RT_DEV int32_t LdI<true>(Base<true> b, uint32_t off)
 {
@@ -139,12 +148,14 @@ template <> RT_DEV int32_t LdI<true>(Base<true> b, uint32_t off)
 template <> RT_DEV int32_t LdI<false>(Base<false> b, uint32_t off) { return __ldg(reinterpret_cast<const int32_t*>(b.a + off)); }
 
 template <bool SMEM> struct SceneView {
-    Base<SMEM> nodes, spheres, sphere_material, moving, quads, media, materials;
+    Base<SMEM> nodes, spheres, sphere_material, moving, quads, media, materials, mat_params;
     // never staged: textures and their tables
     const DevTexture* textures;
     const DevPerlin* perlins;
     const DevImage* images;
     uint32_t root_ref;
+    uint32_t hoisted[RT_MAX_HOISTED]; // leaf refs every ray tests before it enters the tree
+    int n_hoisted;
 };
 
 // Per-thread traversal stack in shared memory: entry(level) = base + level*stride.
@@ -568,10 +579,9 @@ RT_DEV void TraceBox(const SceneView<SMEM>& sv, const RaySlab& slab, float tmin,
 
 // One leaf: a typed run of primitives, or a medium.
 template <int FEAT, bool SMEM>
-RT_DEV void TraceLeaf(const SceneView<SMEM>& sv, const Ray& r, double a, float rcpA, float tmin, const Stack& stack, Trav& tv,
-                      uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
+RT_DEV void TestLeaf(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, double a, float rcpA, float tmin, Trav& tv,
+                     uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
 {
-    const uint32_t ref = tv.ref;
     if ((FEAT & RT_FEAT_MEDIUM) && RT_REF_TYPE(ref) == RT_LEAF_MEDIUM) {
         const uint32_t m = RT_REF_FIRST(ref);
         double tm;
@@ -584,7 +594,27 @@ RT_DEV void TraceLeaf(const SceneView<SMEM>& sv, const Ray& r, double a, float r
         const uint32_t h = HitRun<FEAT, SMEM, float>(sv, ref, r, a, rcpA, tmin, tv.t, primTests);
         if (h != RT_HIT_NONE) tv.hit = h;
     }
+}
+
+template <int FEAT, bool SMEM>
+RT_DEV void TraceLeaf(const SceneView<SMEM>& sv, const Ray& r, double a, float rcpA, float tmin, const Stack& stack, Trav& tv,
+                      uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
+{
+    TestLeaf<FEAT, SMEM>(sv, tv.ref, r, a, rcpA, tmin, tv, seed, pixel, sample, slot, primTests);
     TravPop(stack, tv);
+}
+
+// Starts a walk: the hoisted items (scene-sized primitives / media kept out of the tree, rt_pack.hpp) are tested
+// first -- in a kernel whose lanes start their walks together this is straight-line code on a full warp -- and the
+// distance they return bounds the walk through the tree.
+template <int FEAT, bool SMEM>
+RT_DEV void BeginWalk(const SceneView<SMEM>& sv, const Ray& r, double a, float rcpA, float tmin, const Stack& stack, Trav& tv,
+                      uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
+{
+    tv.Begin(sv.root_ref, stack);
+#pragma unroll
+    for (int k = 0; k < RT_MAX_HOISTED; ++k) // unrolled: the refs stay kernel parameters (constant bank), not a local array
+        if (k < sv.n_hoisted) TestLeaf<FEAT, SMEM>(sv, sv.hoisted[k], r, a, rcpA, tmin, tv, seed, pixel, sample, slot, primTests);
 }
 
 // ----------------------------------------------------------------- textures
@@ -741,24 +771,31 @@ template <int FEAT, bool SMEM>
 RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, const d3& dirIn, double a, bool sphereLike, const StreamKey& rng,
                     f3& atten, d3& dir, f3& emitted)
 {
-    const float4 m0 = Ld4<SMEM>(sv.materials, (uint32_t)h.material * 32u);
-    const float4 m1 = Ld4<SMEM>(sv.materials, (uint32_t)h.material * 32u + 16u);
-    const int type = __float_as_int(m1.x);
-    const int tex = __float_as_int(m1.y);
-    const double param = __hiloint2double(__float_as_int(m1.w), __float_as_int(m1.z)); // fuzz | ior, FP64
+    const float4 m0 = Ld4<SMEM>(sv.materials, (uint32_t)h.material * 16u);
+    const uint32_t tt = (uint32_t)__float_as_int(m0.w);
+    const int type = RT_MAT_TT_TYPE(tt);
+    const bool hasParam = type == RT_MAT_METAL || type == RT_MAT_DIELECTRIC;
+    const int tex = hasParam ? -1 : (int)RT_MAT_TT_INDEX(tt) - 1;
+    double param = 0.0; // fuzz | ior, FP64
+    if (hasParam) param = LdD<SMEM>(sv.mat_params, RT_MAT_TT_INDEX(tt) * 8u);
     emitted = make_f3(0.0f, 0.0f, 0.0f);
     f3 colour = make_f3(m0.x, m0.y, m0.z);
     if ((FEAT & RT_FEAT_TEXTURE) && tex >= 0 && type != RT_MAT_METAL && type != RT_MAT_DIELECTRIC)
         colour = TextureValue<FEAT, SMEM>(sv, tex, h, sphereLike);
+    // Lambertian, Metal and Isotropic all start with RandomInUnitSphere from the top of the slot's stream
+    // (Material.h:75,157, Metal.h:27): ONE rejection loop serves the three, instead of one copy per material that
+    // the lanes of a warp would run one after the other.
+    d3 ball = make_d3(0.0, 0.0, 0.0);
+    if (type == RT_MAT_LAMBERTIAN || type == RT_MAT_METAL || type == RT_MAT_ISOTROPIC) ball = RandomInUnitSphere(rng);
     if (type == RT_MAT_LAMBERTIAN) { // Material.h:68-86
-        dir = h.n + RandomInUnitSphere(rng);
+        dir = h.n + ball;
         if (fabs(dir.x) < 1e-8 && fabs(dir.y) < 1e-8 && fabs(dir.z) < 1e-8) dir = h.n;
         atten = colour;
         return true;
     }
     if (type == RT_MAT_METAL) { // Metal.h:18-30 (draws even when fuzz == 0)
         const d3 reflected = Reflect(RsqrtD(a) * dirIn, h.n);
-        dir = reflected + param * RandomInUnitSphere(rng);
+        dir = reflected + param * ball;
         atten = colour;
         return dot(dir, h.n) > 0.0;
     }
@@ -787,8 +824,7 @@ RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, const d3& dirIn, do
         return true;
     }
     if (type == RT_MAT_ISOTROPIC) { // Material.h:151-162
-        const d3 p = RandomInUnitSphere(rng);
-        dir = RsqrtD(dot(p, p)) * p;
+        dir = RsqrtD(dot(ball, ball)) * ball;
         atten = colour;
         return true;
     }
