@@ -69,22 +69,24 @@ def parse_args():
 
 # ---------------------------------------------------------------- CPU arms
 def load_cpu_reference():
-    """-> (kind, callable(W,H,s0,s1,threads) -> (rays, box, sph, quad, seconds))."""
-    from raytracinginoneweekendincuda_b200 import BuiltinScene, _abi as A, _build
+    """-> (kind, what, callable(W,H,s0,s1,threads) -> (rays, seconds)).  The CPU arm: the reference's own headers
+    compiled for the host, -O3 -march=native (oracle/_ref/libref_stream_fast.so; the -O2 -ffp-contract=off build
+    beside it is the bit-exact pin, not the baseline), else the FP64 oracle port."""
+    from oracle import bindings as O
+    from raytracinginoneweekendincuda_b200 import BuiltinScene
     import numpy as np
-    ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_stream.so")
     sid = ARGS.scene
     earth = None
     if sid in (2, 9):
         from raytracinginoneweekendincuda_b200 import load_earth_fixture
         earth = load_earth_fixture()
-    if os.path.exists(ref_path):
-        lib = C.CDLL(ref_path)
-        A.declare_ref_stream(lib)
-
+    lib, flags = O.load_ref_stream(fast=True), "g++ -O3 -march=native"
+    if lib is None:
+        lib, flags = O.load_ref_stream(fast=False), "g++ -O2 -ffp-contract=off (the pin build; no -O3 build present)"
+    if lib is not None:
         def run_ref(W, H, s0, s1, threads):
             out = np.zeros((H, W, 3), np.float64)
-            st = A.ref_stream_stats()
+            st = O.ref_stream_stats()
             ep, ew, eh = (earth.ctypes.data, earth.shape[1], earth.shape[0]) if earth is not None else (None, 0, 0)
             t0 = time.perf_counter()
             rc = lib.ref_stream_render(sid, W, H, s0, s1, WORKLOAD["max_depth"], SEED, ep, ew, eh, threads,
@@ -92,44 +94,40 @@ def load_cpu_reference():
             dt = time.perf_counter() - t0
             assert rc == 0
             return int(st.rays), dt
-        return "reference", run_ref
-    if not os.path.exists(_build.oracle_path()):
-        _build.build_oracle()
-    lib = C.CDLL(_build.oracle_path())
-    A.declare_oracle(lib)
+        return "reference", f"reference headers (FP64) compiled for the host by {flags}, row-parallel std::thread", run_ref
+    lib = O.load_oracle()
     sc = BuiltinScene(sid, earth)
 
     def run_port(W, H, s0, s1, threads):
         cam = sc.camera(W, H, WORKLOAD["spp"], WORKLOAD["max_depth"])
         out = np.zeros((H, W, 3), np.float64)
-        st = A.oracle_stats()
+        st = O.oracle_stats()
         t0 = time.perf_counter()
         rc = lib.oracle_render(sc.desc, C.byref(cam), s0, s1, SEED, 1, 64, threads, out.ctypes.data, C.byref(st))
         dt = time.perf_counter() - t0
         assert rc == 0
         return int(st.rays), dt
-    return "port", run_port
+    return "port", "oracle/rt_oracle.cpp (FP64 restatement, g++ -O2 -ffp-contract=off), row-parallel std::thread", run_port
 
 
-def reference_topology_counts():
+def reference_topology_counts(scene_id=None):
     """n_box, n_sphere, n_quad per ray on the reference-topology BVH, measured by the
     FP64 oracle on a small sample of the workload (the algorithmic work definition
     of SURVEY.md 8d is implementation independent)."""
-    from raytracinginoneweekendincuda_b200 import BuiltinScene, _abi as A, _build
+    from oracle import bindings as O
+    from raytracinginoneweekendincuda_b200 import BuiltinScene
     import numpy as np
-    if not os.path.exists(_build.oracle_path()):
-        _build.build_oracle()
-    lib = C.CDLL(_build.oracle_path())
-    A.declare_oracle(lib)
+    lib = O.load_oracle()
+    sid = ARGS.scene if scene_id is None else scene_id
     earth = None
-    if ARGS.scene in (2, 9):
+    if sid in (2, 9):
         from raytracinginoneweekendincuda_b200 import load_earth_fixture
         earth = load_earth_fixture()
-    sc = BuiltinScene(ARGS.scene, earth)
+    sc = BuiltinScene(sid, earth)
     W, H = 480, 270
     cam = sc.camera(W, H, 1, WORKLOAD["max_depth"])
     out = np.zeros((H, W, 3), np.float64)
-    st = A.oracle_stats()
+    st = O.oracle_stats()
     lib.oracle_render(sc.desc, C.byref(cam), 0, 1, SEED, 1, 64, os.cpu_count() or 1, out.ctypes.data, C.byref(st))
     r = max(1, st.rays)
     return {"n_box": st.box_tests / r, "n_sphere": st.sphere_tests / r, "n_quad": st.quad_tests / r,
@@ -137,16 +135,14 @@ def reference_topology_counts():
 
 
 def cpu_baseline(budget_s=12.0):
-    kind, run = load_cpu_reference()
+    kind, what, run = load_cpu_reference()
     cores = os.cpu_count() or 1
     W, H = ARGS.width, ARGS.height
     rays1, t1 = run(W, H, 0, 1, cores)  # calibration sample
     n = int(max(1, min(16, round(budget_s / max(t1, 1e-3)))))
     rays, dt = run(W, H, 1, 1 + n, cores)
     return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
-            "sample": f"{W}x{H}, samples [1,{1 + n}) of {ARGS.spp}, {rays} rays in {dt:.2f} s",
-            "what": "reference headers (FP64) compiled for the host by g++ -O2, row-parallel std::thread"
-                    if kind == "reference" else "oracle/rt_oracle.cpp (FP64 restatement), row-parallel std::thread"}
+            "sample": f"{W}x{H}, samples [1,{1 + n}) of {ARGS.spp}, {rays} rays in {dt:.2f} s", "what": what}
 
 
 def gpu_reference():
@@ -172,7 +168,7 @@ def run_reference_arm():
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    kind, run = load_cpu_reference()
+    kind, what, run = load_cpu_reference()
     cores = os.cpu_count() or 1
     W, H = ARGS.width, ARGS.height
     # one step = one sample per pixel of the frame (1/spp of the workload), all host threads
@@ -190,7 +186,7 @@ def run_reference_arm():
         "n_gpus": ARGS.gpus, "steps": ARGS.steps, "warmup": ARGS.warmup, "ms_per_step": total_t / ARGS.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(1),
-        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample, "what": what},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

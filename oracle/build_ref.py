@@ -11,8 +11,10 @@ repository and never written into the tree.  Outputs:
         (Vec3.h .. Camera.h) compiled for the HOST by g++ through the shims in
         oracle/shim/, plus CreateWorld (kernel.cu:157-545) as text, driven by
         oracle/ref_stream_main.cpp.  Random numbers come from the render path's
-        counter-based stream.  This is what pins oracle/rt_oracle.cpp, and it is
-        the CPU baseline ("kind": "reference") of bench.py.
+        counter-based stream.  Built -O2 -ffp-contract=off: this is what pins
+        oracle/rt_oracle.cpp bit for bit.
+  oracle/_ref/libref_stream_fast.so  the same sources built -O3 -march=native:
+        the CPU baseline ("kind": "reference") that bench.py times.
   oracle/_ref/ref_gpu           the reference's kernel.cu for sm_100 with its
         hard-coded constants turned into argv, a ray counter and cudaEvent
         timing: the GPU baseline the >=10x target is measured against, and the
@@ -163,6 +165,12 @@ def build_ref_stream(tmp: str) -> None:
          "-I", tmp, "-I", os.path.join(HERE, "shim"),
          os.path.join(HERE, "ref_stream_main.cpp"), os.path.join(HERE, "ref_image.cpp"),
          os.path.join(tmp, "stb.o"), "-o", os.path.join(OUT, "libref_stream.so")])
+    # The same sources as an optimised build: the CPU BASELINE of bench.py (-O3 -march=native).  Not a
+    # pin: contraction and vectorisation may change last bits; tests/test_oracle_pin.py checks it stays within 1e-9.
+    run(["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w",
+         "-I", tmp, "-I", os.path.join(HERE, "shim"),
+         os.path.join(HERE, "ref_stream_main.cpp"), os.path.join(HERE, "ref_image.cpp"),
+         os.path.join(tmp, "stb.o"), "-o", os.path.join(OUT, "libref_stream_fast.so")])
 
 
 GPU_PROLOGUE = r'''

@@ -822,15 +822,21 @@ V3<R> RayColor(const Scene<R>& s, const Cam<R>& cam, Ray<R> ray, Stream& rng, bo
 // kernel.cu:122-154, one row.  Output is the linear SUM over the samples
 // rendered (the reference divides by numSamples and takes sqrt afterwards,
 // :147-152; parity is defined on linear radiance).
+// Window: pixels [x0, x0+w) x [y0, y0+h) of the W x H frame.  Pixel indices (and so the random streams) are the
+// GLOBAL ones, pixel = j*W + i; `out` holds only the window, row-major, w*h*3.
+struct Window {
+    int x0, y0, w, h;
+};
+
 template <class R>
-void RenderRows(const Scene<R>& s, const Cam<R>& cam, int j0, int j1, int s0, int s1, uint32_t seed, bool useBvh,
-                double* out, Stats& st)
+void RenderRows(const Scene<R>& s, const Cam<R>& cam, const Window& win, int j0, int j1, int s0, int s1, uint32_t seed,
+                bool useBvh, double* out, Stats& st)
 {
     Stream rng;
     rng.seed = seed;
     rng.stats = &st;
     for (int j = j0; j < j1; ++j) {
-        for (int i = 0; i < cam.W; ++i) {
+        for (int i = win.x0; i < win.x0 + win.w; ++i) {
             const int pixel = j * cam.W + i;
             rng.pixel = (uint32_t)pixel;
             V3<R> col(0, 0, 0);
@@ -846,29 +852,33 @@ void RenderRows(const Scene<R>& s, const Cam<R>& cam, int j0, int j1, int s0, in
                 const Ray<R> r = cam.GetRay(u, v, rng);
                 col = col + RayColor(s, cam, r, rng, useBvh, st);
             }
-            out[(size_t)pixel * 3 + 0] = (double)col[0];
-            out[(size_t)pixel * 3 + 1] = (double)col[1];
-            out[(size_t)pixel * 3 + 2] = (double)col[2];
+            double* o = out + ((size_t)(j - win.y0) * win.w + (size_t)(i - win.x0)) * 3;
+            o[0] = (double)col[0];
+            o[1] = (double)col[1];
+            o[2] = (double)col[2];
         }
     }
 }
 
 template <class R>
-int RenderT(const rt_scene_desc* d, const rt_camera* c, int s0, int s1, uint32_t seed, bool useBvh, int nThreads,
-            double* out, Stats& total)
+int RenderT(const rt_scene_desc* d, const rt_camera* c, const Window* window, int s0, int s1, uint32_t seed, bool useBvh,
+            int nThreads, double* out, Stats& total)
 {
     Scene<R> s;
     if (!LoadScene(d, s)) return -1;
     const Cam<R> cam(*c);
     if (nThreads < 1) nThreads = 1;
     std::vector<Stats> st((size_t)nThreads);
-    std::atomic<int> nextRow(0);
-    const int rowsPerGrab = 4;
+    Window win{0, 0, cam.W, cam.H};
+    if (window) win = *window;
+    if (win.x0 < 0 || win.y0 < 0 || win.w <= 0 || win.h <= 0 || win.x0 + win.w > cam.W || win.y0 + win.h > cam.H) return -2;
+    std::atomic<int> nextRow(win.y0);
+    const int rowsPerGrab = 4, rowEnd = win.y0 + win.h;
     auto work = [&](int tid) {
         while (true) {
             const int j0 = nextRow.fetch_add(rowsPerGrab);
-            if (j0 >= cam.H) break;
-            RenderRows(s, cam, j0, std::min(cam.H, j0 + rowsPerGrab), s0, s1, seed, useBvh, out, st[(size_t)tid]);
+            if (j0 >= rowEnd) break;
+            RenderRows(s, cam, win, j0, std::min(rowEnd, j0 + rowsPerGrab), s0, s1, seed, useBvh, out, st[(size_t)tid]);
         }
     };
     std::vector<std::thread> pool;
@@ -892,16 +902,38 @@ struct oracle_stats {
 // out: W*H*3 doubles, row 0 = bottom row, linear radiance SUM over [s0,s1).
 // bvh: 1 = reference-topology BVH (BvhNode.h), 0 = linear list.
 // precision: 64 = the oracle; 32 = float study build of the same code.
+static int OracleRender(const rt_scene_desc* scene, const rt_camera* cam, const Window* win, int sample_begin,
+                        int sample_end, uint32_t seed, int bvh, int precision, int n_threads, double* out,
+                        struct oracle_stats* stats);
+
 int oracle_render(const rt_scene_desc* scene, const rt_camera* cam, int sample_begin, int sample_end, uint32_t seed,
                   int bvh, int precision, int n_threads, double* out, oracle_stats* stats)
+{
+    return OracleRender(scene, cam, nullptr, sample_begin, sample_end, seed, bvh, precision, n_threads, out, stats);
+}
+
+// The same for a pixel window of the frame: out = w*h*3 doubles (row 0 = the window's bottom row).  The streams are
+// keyed on the GLOBAL pixel index, so the window of a 4K frame is rendered exactly as the full frame would render it,
+// at the cost of the window only (full-size parity checks of the BASELINE configs).
+int oracle_render_region(const rt_scene_desc* scene, const rt_camera* cam, int x0, int y0, int w, int h,
+                         int sample_begin, int sample_end, uint32_t seed, int bvh, int precision, int n_threads,
+                         double* out, oracle_stats* stats)
+{
+    const Window win{x0, y0, w, h};
+    return OracleRender(scene, cam, &win, sample_begin, sample_end, seed, bvh, precision, n_threads, out, stats);
+}
+
+static int OracleRender(const rt_scene_desc* scene, const rt_camera* cam, const Window* win, int sample_begin,
+                        int sample_end, uint32_t seed, int bvh, int precision, int n_threads, double* out,
+                        oracle_stats* stats)
 {
     if (!scene || !cam || !out || cam->image_width <= 0 || cam->image_height <= 0) return -1;
     Stats st;
     int rc;
     if (precision == 32)
-        rc = RenderT<float>(scene, cam, sample_begin, sample_end, seed, bvh != 0, n_threads, out, st);
+        rc = RenderT<float>(scene, cam, win, sample_begin, sample_end, seed, bvh != 0, n_threads, out, st);
     else
-        rc = RenderT<double>(scene, cam, sample_begin, sample_end, seed, bvh != 0, n_threads, out, st);
+        rc = RenderT<double>(scene, cam, win, sample_begin, sample_end, seed, bvh != 0, n_threads, out, st);
     if (rc != 0) return rc;
     if (stats) {
         std::memset(stats, 0, sizeof *stats);

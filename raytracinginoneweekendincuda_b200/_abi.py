@@ -110,20 +110,6 @@ class rt_pack_info(C.Structure):
                 ("hoisted", C.c_uint32 * 4), ("staged_bytes", C.c_uint64)]
 
 
-# oracle/rt_oracle.cpp
-class oracle_stats(C.Structure):
-    _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("box_tests", C.c_uint64),
-                ("sphere_tests", C.c_uint64), ("quad_tests", C.c_uint64), ("medium_tests", C.c_uint64),
-                ("draws", C.c_uint64), ("n_nodes", C.c_int32), ("n_objects", C.c_int32),
-                ("medium_visits", C.c_int32 * 8)]
-
-
-# oracle/ref_stream_main.cpp
-class ref_stream_stats(C.Structure):
-    _fields_ = [("rays", C.c_ulonglong), ("paths", C.c_ulonglong), ("draws", C.c_ulonglong),
-                ("scene_draws", C.c_ulonglong), ("n_objects", C.c_int), ("n_nodes", C.c_int)]
-
-
 def declare_host(lib: C.CDLL) -> None:
     """Prototypes of the host-only entry points (no CUDA call behind them)."""
     lib.rt_last_error.restype = C.c_char_p
@@ -178,30 +164,3 @@ def declare_device(lib: C.CDLL) -> None:
     lib.rt_release_cached_memory.argtypes = []
     lib.rt_abi_sizeof.restype = C.c_int
     lib.rt_abi_sizeof.argtypes = [C.c_char_p]
-
-
-def declare_oracle(lib: C.CDLL) -> None:
-    lib.oracle_render.restype = C.c_int
-    lib.oracle_render.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_camera), C.c_int, C.c_int, C.c_uint32,
-                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(oracle_stats)]
-    lib.oracle_trace_path.restype = C.c_int
-    lib.oracle_trace_path.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_camera), C.c_int, C.c_int, C.c_int,
-                                      C.c_uint32, C.c_void_p, C.c_int]
-    lib.oracle_rng_uniform.restype = C.c_float
-    lib.oracle_rng_uniform.argtypes = [C.c_uint32] * 6
-    lib.oracle_bvh_topology.restype = C.c_int
-    lib.oracle_bvh_topology.argtypes = [C.POINTER(rt_scene_desc), C.c_void_p, C.c_int32]
-    lib.oracle_texture_value.restype = C.c_int
-    lib.oracle_texture_value.argtypes = [C.POINTER(rt_scene_desc), C.c_int, C.c_double, C.c_double, C.c_void_p,
-                                         C.c_void_p]
-
-
-def declare_ref_stream(lib: C.CDLL) -> None:
-    lib.ref_stream_render.restype = C.c_int
-    lib.ref_stream_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p,
-                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(ref_stream_stats)]
-    lib.ref_stream_scene_boxes.restype = C.c_int
-    lib.ref_stream_scene_boxes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                           C.c_int, C.POINTER(C.c_ulonglong)]
-    lib.ref_load_image_rgb8.restype = C.c_int
-    lib.ref_load_image_rgb8.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_int]

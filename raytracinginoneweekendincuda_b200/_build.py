@@ -2,8 +2,7 @@
 
   librt_b200.so  (this package dir)  the product: C ABI + kernels + host scene surface
   rt_cli         (this package dir)  command-line renderer (PPM out)
-  oracle/liboracle.so                the FP64 checker (tests / bench baseline only)
-  oracle/_ref/*                      reference-derived checkers, only where /root/reference exists
+The checker (oracle/) has its own recipes in oracle/bindings.py; CMakeLists.txt builds the same two targets.
 """
 from __future__ import annotations
 
@@ -43,18 +42,21 @@ def lib_path() -> str:
     return os.path.join(PKG, "librt_b200.so")
 
 
-def oracle_path() -> str:
-    return os.path.join(ROOT, "oracle", "liboracle.so")
-
-
-def build_product(force: bool = False, verbose_ptxas: bool = False) -> str:
+def build_product(force: bool = False, verbose_ptxas: bool = False, target: str | None = None,
+                  defines: list[str] | None = None) -> str:
+    """`target` / `defines`: an A/B build of the library with -D options into another file (load it with
+    RT_B200_LIBRARY); the default builds the in-tree product and the CLI."""
     deps = _sources([CSRC, os.path.join(ROOT, "include")])
-    target = lib_path()
-    if force or not _newer(target, deps):
+    variant = target is not None
+    target = target or lib_path()
+    if force or variant or not _newer(target, deps):
         extra = ["-Xptxas", "-v"] if verbose_ptxas else []
+        extra += [f"-D{d}" for d in (defines or [])]
         _run(["nvcc", *NVCC_FLAGS, *extra, "-shared",
               os.path.join(CSRC, "rt_device.cu"), os.path.join(CSRC, "rt_host.cpp"),
               os.path.join(CSRC, "rt_error.cpp"), "-o", target])
+    if variant:
+        return target
     cli = os.path.join(PKG, "rt_cli")
     if force or not _newer(cli, deps):
         _run(["nvcc", *NVCC_FLAGS, os.path.join(CSRC, "rt_cli.cpp"), "-o", cli, "-L", PKG, "-lrt_b200",
@@ -62,32 +64,8 @@ def build_product(force: bool = False, verbose_ptxas: bool = False) -> str:
     return target
 
 
-def build_oracle(force: bool = False) -> str:
-    src = os.path.join(ROOT, "oracle", "rt_oracle.cpp")
-    target = oracle_path()
-    if force or not _newer(target, [src, os.path.join(ROOT, "include", "rt_abi.h")]):
-        _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-pthread", "-Wall", "-Wextra",
-              src, "-o", target])
-    return target
-
-
-def build_ref() -> None:
-    """oracle/_ref from /root/reference, when it is there (build container only)."""
-    if not os.path.isdir(os.environ.get("RT_REFERENCE_DIR", "/root/reference")):
-        return
-    out = os.path.join(ROOT, "oracle", "_ref")
-    need = [os.path.join(out, "libref_stream.so"), os.path.join(out, "ref_gpu")]
-    srcs = [os.path.join(ROOT, "oracle", f) for f in ("build_ref.py", "ref_stream_main.cpp", "ref_image.cpp")]
-    srcs += _sources([os.path.join(ROOT, "oracle", "shim")])
-    if all(_newer(t, srcs) for t in need):
-        return
-    _run([sys.executable, os.path.join(ROOT, "oracle", "build_ref.py")])
-
-
 def build_all(force: bool = False) -> None:
     build_product(force)
-    build_oracle(force)
-    build_ref()
 
 
 if __name__ == "__main__":

@@ -54,9 +54,10 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
     const int nTiles = args.tilesX * args.tilesY;
     const f3 background = make_f3(cam.background[0], cam.background[1], cam.background[2]);
     const uint32_t leafMask = (uint32_t)args.megaLeafMask;
-    unsigned long long nRays = 0, nPaths = 0, nNode = 0, nPrim = 0;
+    unsigned long long nPaths = 0, nNode = 0, nPrim = 0;
 
     while (true) {
+        uint32_t nRays = 0; // per tile: a 64-bit running count would sit in two registers (or a spill slot) all the way
         int tile = 0;
         if (lane == 0) tile = (int)atomicAdd(args.tileCounter, 1u);
         tile = __shfl_sync(FULL, tile, 0);
@@ -226,11 +227,12 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
             px[1] += SUM[32 + lane];
             px[2] += SUM[64 + lane];
         }
+        nRays = __reduce_add_sync(FULL, nRays);
+        if (lane == 0) atomicAdd(&args.stats[0], (unsigned long long)nRays);
         __syncwarp();
     }
 
     for (int off = 16; off > 0; off >>= 1) {
-        nRays += __shfl_down_sync(FULL, nRays, off);
         if (STATS) {
             nPaths += __shfl_down_sync(FULL, nPaths, off);
             nNode += __shfl_down_sync(FULL, nNode, off);
@@ -238,7 +240,6 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
         }
     }
     if (lane == 0) {
-        atomicAdd(&args.stats[0], nRays);
         if (STATS) {
             atomicAdd(&args.stats[1], nPaths);
             atomicAdd(&args.stats[2], nNode);

@@ -46,6 +46,23 @@ __device__ __forceinline__ uint32_t Stage(uint32_t& cursor, char* smem, const vo
     return at;
 }
 
+// The node table on its way into shared memory: the ref of an internal node (index of its child pair) becomes the
+// pair's shared ADDRESS, so a traversal step loads from [ref + imm] without a base register or a shift.  Leaf refs
+// (bit 31 set) stay as they are; shared addresses never reach bit 31.
+__device__ __forceinline__ uint32_t StageNodes(uint32_t& cursor, char* smem, uint32_t smemBase, const void* src, uint32_t bytes)
+{
+    const uint32_t at = cursor;
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(smem + at);
+    for (uint32_t k = threadIdx.x; k < bytes / 16u; k += blockDim.x) {
+        uint4 v = __ldg(&s[k]);
+        if ((k & 1u) == 0u && !(v.w & RT_REF_LEAF)) v.w = smemBase + at + v.w * 32u; // DevNode: {c.xyz, ref}{e.xyz, aux}
+        d[k] = v;
+    }
+    cursor += (bytes + 15u) & ~15u;
+    return at;
+}
+
 // Stages the scene arrays in shared memory (SMEM) or points at them in global memory.
 template <bool SMEM>
 __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, const RenderArgs& args, char* smem, uint32_t smemBase,
@@ -53,7 +70,7 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
 {
     SceneView<SMEM> sv;
     if constexpr (SMEM) {
-        sv.nodes.a = smemBase + Stage(cursor, smem, scene.nodes, args.nodesBytes);
+        sv.nodes.a = smemBase + StageNodes(cursor, smem, smemBase, scene.nodes, args.nodesBytes);
         sv.spheres.a = smemBase + Stage(cursor, smem, scene.spheres, args.spheresBytes);
         sv.sphere_material.a = smemBase + Stage(cursor, smem, scene.sphere_material, args.sphereMatBytes);
         sv.moving.a = smemBase + Stage(cursor, smem, scene.moving, args.movingBytes);
@@ -76,6 +93,8 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
     sv.perlins = scene.perlins;
     sv.images = scene.images;
     sv.root_ref = scene.root_ref;
+    if constexpr (SMEM)
+        if (!(sv.root_ref & RT_REF_LEAF)) sv.root_ref = sv.nodes.a + sv.root_ref * 32u;
     sv.n_hoisted = scene.n_hoisted;
 #pragma unroll
     for (int k = 0; k < RT_MAX_HOISTED; ++k) sv.hoisted[k] = scene.hoisted[k];

@@ -158,18 +158,21 @@ template <bool SMEM> struct SceneView {
     int n_hoisted;
 };
 
-// Per-thread traversal stack in shared memory: entry(level) = base + level*stride.
+// Per-thread traversal stack in shared memory, [level][thread]: entry(level) = base + level*stride, so the lanes of
+// a warp never share a bank.  The walk keeps the ADDRESS of its next free entry (Trav::sp), not a level index: a
+// push is one store and one add, a pop one add and one load (the index form cost an IMAD and a re-read of the thread
+// id per access -- the compiler rematerialised the base inside the loop rather than spend a register on it).
 struct Stack {
     uint32_t base;   // shared address of this thread's level-0 slot
     uint32_t stride; // bytes between levels = 4*blockDim.x
-    RT_DEV void Push(int sp, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + sp * stride), "r"(v)); }
-    RT_DEV uint32_t Pop(int sp) const
-    {
-        uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + sp * stride));
-        return v;
-    }
 };
+RT_DEV void StackStore(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
+RT_DEV uint32_t StackLoad(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 // ---------------------------------------------------------------------- ray
 struct Ray {
@@ -179,9 +182,17 @@ struct Ray {
 };
 
 // What traversal needs besides the ray: fp32 copies for the slab test.
+// RT_SLAB_FFMA (build option, A/B): also keep |1/d|, so that entry/exit = fma(-+e, |1/d|, t_centre) -- 9 FFMA per box
+// instead of 3 FFMA + 3 FMUL + 6 FADD -- at the price of three more live registers in the traversal loop.
+#ifndef RT_SLAB_FFMA
+#define RT_SLAB_FFMA 0
+#endif
 struct RaySlab {
     f3 inv;     // 1/d
     f3 ood;     // o/d
+#if RT_SLAB_FFMA
+    f3 ainv;    // |1/d|
+#endif
     float rcpA; // 1/|d|^2, for the sphere roots
 };
 
@@ -194,6 +205,9 @@ RT_DEV RaySlab MakeSlab(const Ray& r)
     s.inv = make_f3(RcpApprox(df.x), RcpApprox(df.y), RcpApprox(df.z));
     s.rcpA = RcpApprox(fmaf(df.x, df.x, fmaf(df.y, df.y, df.z * df.z)));
     s.ood = make_f3((float)r.o.x * s.inv.x, (float)r.o.y * s.inv.y, (float)r.o.z * s.inv.z);
+#if RT_SLAB_FFMA
+    s.ainv = make_f3(fabsf(s.inv.x), fabsf(s.inv.y), fabsf(s.inv.z));
+#endif
     return s;
 }
 
@@ -203,11 +217,18 @@ RT_DEV RaySlab MakeSlab(const Ray& r)
 // [tmin, tmax]; `tn` is the entry distance.
 RT_DEV bool SlabEntry(const float4 c, const float4 e, const RaySlab& s, float tmin, float tmax, float& tn)
 {
-    const float cx = fmaf(c.x, s.inv.x, -s.ood.x), px = fabsf(e.x * s.inv.x);
-    const float cy = fmaf(c.y, s.inv.y, -s.ood.y), py = fabsf(e.y * s.inv.y);
-    const float cz = fmaf(c.z, s.inv.z, -s.ood.z), pz = fabsf(e.z * s.inv.z);
+    const float cx = fmaf(c.x, s.inv.x, -s.ood.x);
+    const float cy = fmaf(c.y, s.inv.y, -s.ood.y);
+    const float cz = fmaf(c.z, s.inv.z, -s.ood.z);
+#if RT_SLAB_FFMA
+    // e * |1/d| = NaN only for 0 * inf (a flat box seen edge-on): fminf/fmaxf drop it, like the product form below
+    tn = fmaxf(fmaxf(fmaf(-e.x, s.ainv.x, cx), fmaf(-e.y, s.ainv.y, cy)), fmaxf(fmaf(-e.z, s.ainv.z, cz), tmin));
+    const float tf = fminf(fminf(fmaf(e.x, s.ainv.x, cx), fmaf(e.y, s.ainv.y, cy)), fminf(fmaf(e.z, s.ainv.z, cz), tmax));
+#else
+    const float px = fabsf(e.x * s.inv.x), py = fabsf(e.y * s.inv.y), pz = fabsf(e.z * s.inv.z);
     tn = fmaxf(fmaxf(cx - px, cy - py), fmaxf(cz - pz, tmin));
     const float tf = fminf(fminf(cx + px, cy + py), fminf(cz + pz, tmax));
+#endif
     return tf >= tn;
 }
 
@@ -320,6 +341,7 @@ RT_DEV uint32_t HitRun(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, do
 {
     const uint32_t type = RT_REF_TYPE(ref), first = RT_REF_FIRST(ref), count = RT_REF_COUNT(ref);
     uint32_t hit = RT_HIT_NONE;
+#pragma unroll 1 // leaves hold 1-2 primitives: an unrolled body only bloats the divergent leaf path
     for (uint32_t i = 0; i < count; ++i) {
         float t;
         ++primTests;
@@ -527,8 +549,10 @@ RT_DEV bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, d
 // lanes that are shading or starting a new path.
 #define RT_TRAV_DONE 0xffffffffu
 struct Trav {
-    uint32_t ref; // node / leaf to visit next, RT_TRAV_DONE when the walk is over
-    int sp;
+    uint32_t ref; // node / leaf to visit next, RT_TRAV_DONE when the walk is over.  Internal node: index of its child
+                  // pair (scene in global memory) or the pair's shared-memory ADDRESS (scene staged: SetupScene
+                  // rewrites the refs while it copies the nodes, so a visit needs no base and no shift)
+    uint32_t sp;  // shared address of the next free stack entry
     float t;      // closest hit so far (fp32; refined by FinalizeHit)
     uint32_t hit; // RT_HIT_* id or RT_HIT_NONE
     double tMedium; // FP64 scatter distance when `hit` is a medium
@@ -536,8 +560,8 @@ struct Trav {
     RT_DEV void Begin(uint32_t root, const Stack& stack)
     {
         ref = root;
-        stack.Push(0, RT_TRAV_DONE);
-        sp = 1;
+        StackStore(stack.base, RT_TRAV_DONE);
+        sp = stack.base + stack.stride;
         t = 3.402823466e+38f;
         hit = RT_HIT_NONE;
     }
@@ -550,17 +574,43 @@ struct Trav {
     }
 };
 
-RT_DEV void TravPop(const Stack& stack, Trav& tv) { tv.ref = stack.Pop(--tv.sp); }
+RT_DEV void TravPop(const Stack& stack, Trav& tv)
+{
+    tv.sp -= stack.stride;
+    tv.ref = StackLoad(tv.sp);
+}
+RT_DEV void TravPush(const Stack& stack, Trav& tv, uint32_t v)
+{
+    StackStore(tv.sp, v);
+    tv.sp += stack.stride;
+}
+
+// The child pair of an internal node: four 128-bit loads.
+template <bool SMEM> RT_DEV void LoadPair(const SceneView<SMEM>& sv, uint32_t ref, float4& lo0, float4& hi0, float4& lo1, float4& hi1);
+template <> RT_DEV void LoadPair<true>(const SceneView<true>&, uint32_t ref, float4& lo0, float4& hi0, float4& lo1, float4& hi1)
+{
+    Base<true> b;
+    b.a = ref; // already an address
+    lo0 = Ld4<true>(b, 0u);
+    hi0 = Ld4<true>(b, 16u);
+    lo1 = Ld4<true>(b, 32u);
+    hi1 = Ld4<true>(b, 48u);
+}
+template <> RT_DEV void LoadPair<false>(const SceneView<false>& sv, uint32_t ref, float4& lo0, float4& hi0, float4& lo1, float4& hi1)
+{
+    const uint32_t off = ref * 32u;
+    lo0 = Ld4<false>(sv.nodes, off);
+    hi0 = Ld4<false>(sv.nodes, off + 16u);
+    lo1 = Ld4<false>(sv.nodes, off + 32u);
+    hi1 = Ld4<false>(sv.nodes, off + 48u);
+}
 
 // One internal node: both children boxes tested, nearer one entered first.
 template <bool SMEM>
 RT_DEV void TraceBox(const SceneView<SMEM>& sv, const RaySlab& slab, float tmin, const Stack& stack, Trav& tv, uint32_t& nodeTests)
 {
-    const uint32_t off = tv.ref * 32u;
-    const float4 lo0 = Ld4<SMEM>(sv.nodes, off);
-    const float4 hi0 = Ld4<SMEM>(sv.nodes, off + 16u);
-    const float4 lo1 = Ld4<SMEM>(sv.nodes, off + 32u);
-    const float4 hi1 = Ld4<SMEM>(sv.nodes, off + 48u);
+    float4 lo0, hi0, lo1, hi1;
+    LoadPair<SMEM>(sv, tv.ref, lo0, hi0, lo1, hi1);
     nodeTests += 2;
     float e0, e1;
     const bool h0 = SlabEntry(lo0, hi0, slab, tmin, tv.t, e0);
@@ -568,7 +618,7 @@ RT_DEV void TraceBox(const SceneView<SMEM>& sv, const RaySlab& slab, float tmin,
     const uint32_t r0 = (uint32_t)__float_as_int(lo0.w), r1 = (uint32_t)__float_as_int(lo1.w);
     if (h0 && h1) {
         const bool swap = e1 < e0;
-        stack.Push(tv.sp++, swap ? r0 : r1);
+        TravPush(stack, tv, swap ? r0 : r1);
         tv.ref = swap ? r1 : r0;
     } else if (h0 || h1) {
         tv.ref = h0 ? r0 : r1;

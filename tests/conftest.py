@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+from oracle import bindings as O  # noqa: E402  (the checker's bindings live with the checker)
 from raytracinginoneweekendincuda_b200 import _abi as A  # noqa: E402
 from raytracinginoneweekendincuda_b200 import _build  # noqa: E402
 
@@ -31,9 +32,10 @@ def pytest_configure(config):
 def built():
     """Make sure the in-tree libraries exist (compiles them when a toolchain is here)."""
     cli = os.path.join(ROOT, "raytracinginoneweekendincuda_b200", "rt_cli")
-    if not (os.path.exists(_build.lib_path()) and os.path.exists(_build.oracle_path()) and os.path.exists(cli)):
+    if not (os.path.exists(_build.lib_path()) and os.path.exists(cli)):
         _build.build_product()
-        _build.build_oracle()
+    if not os.path.exists(O.oracle_path()):
+        O.build_oracle()
     return True
 
 
@@ -45,19 +47,15 @@ def lib(built):
 
 @pytest.fixture(scope="session")
 def oracle(built):
-    o = C.CDLL(_build.oracle_path())
-    A.declare_oracle(o)
-    return o
+    return O.load_oracle()
 
 
 @pytest.fixture(scope="session")
 def ref_stream():
     """The reference's own classes compiled for the host (only where oracle/_ref was built)."""
-    path = os.path.join(ROOT, "oracle", "_ref", "libref_stream.so")
-    if not os.path.exists(path):
+    r = O.load_ref_stream()
+    if r is None:
         pytest.skip("oracle/_ref/libref_stream.so not built (needs /root/reference)")
-    r = C.CDLL(path)
-    A.declare_ref_stream(r)
     return r
 
 
@@ -71,7 +69,7 @@ def earth():
 
 def oracle_render(oracle, scene, cam, s0, s1, seed=1984, bvh=1, precision=64, threads=0):
     out = np.zeros((cam.image_height, cam.image_width, 3), np.float64)
-    st = A.oracle_stats()
+    st = O.oracle_stats()
     rc = oracle.oracle_render(scene.desc, C.byref(cam), s0, s1, seed, bvh, precision, threads or (os.cpu_count() or 1),
                               out.ctypes.data, C.byref(st))
     assert rc == 0
@@ -84,3 +82,13 @@ def has_gpu() -> bool:
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+def oracle_render_region(oracle, scene, cam, x0, y0, w, h, s0, s1, seed=1984, bvh=1, threads=0):
+    """Window [x0,x0+w) x [y0,y0+h) of the frame, streams keyed on the global pixel index: (sum[h,w,3], stats)."""
+    out = np.zeros((h, w, 3), np.float64)
+    st = O.oracle_stats()
+    rc = oracle.oracle_render_region(scene.desc, C.byref(cam), x0, y0, w, h, s0, s1, seed, bvh, 64,
+                                     threads or (os.cpu_count() or 1), out.ctypes.data, C.byref(st))
+    assert rc == 0
+    return out, st

@@ -23,14 +23,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from raytracinginoneweekendincuda_b200 import _abi as A  # noqa: E402
+from oracle import bindings as O  # noqa: E402
 
 W, H, SPP, DEPTH, SEED = 48, 27, 2, 50, 1984
 
 
 def main():
-    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_stream.so"))
-    A.declare_ref_stream(ref)
+    ref = O.load_ref_stream()
     jpg = os.path.join(os.environ.get("RT_REFERENCE_DIR", "/root/reference"), "earthmap.jpg").encode()
     w, h = C.c_int(), C.c_int()
     assert ref.ref_load_image_rgb8(jpg, C.byref(w), C.byref(h), None, 0) == 0
@@ -39,7 +38,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "earthmap_rgb8.npz"), rgb=earth)
     for sid in range(11):
         out = np.zeros((H, W, 3), np.float64)
-        st = A.ref_stream_stats()
+        st = O.ref_stream_stats()
         ref.ref_stream_render(sid, W, H, 0, SPP, DEPTH, SEED, earth.ctypes.data, w.value, h.value, 4,
                               out.ctypes.data, C.byref(st))
         boxes = np.zeros((4096, 6), np.float64)

@@ -13,8 +13,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import ROOT, A
-from raytracinginoneweekendincuda_b200 import _build
+from conftest import ROOT, A, O
+
 from raytracinginoneweekendincuda_b200.multigpu import reduce_accumulators, sample_range
 
 
@@ -37,13 +37,13 @@ def _worker(rank, world, port, spp, W, H, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from raytracinginoneweekendincuda_b200 import BuiltinScene
-    oracle = C.CDLL(_build.oracle_path())
-    A.declare_oracle(oracle)
+    from oracle import bindings as O
+    oracle = O.load_oracle()
     sc = BuiltinScene(10)
     cam = sc.camera(W, H, spp, 50)
     s0, s1 = sample_range(rank, world, spp)
     out = np.zeros((H, W, 3))
-    st = A.oracle_stats()
+    st = O.oracle_stats()
     oracle.oracle_render(sc.desc, C.byref(cam), s0, s1, 1984, 1, 64, 1, out.ctypes.data, C.byref(st))
     acc = torch.from_numpy(out.astype(np.float32))
     rays = torch.tensor([st.rays], dtype=torch.int64)
@@ -74,7 +74,7 @@ def test_two_rank_split_equals_single_render(oracle):
     sc = BuiltinScene(10)
     cam = sc.camera(W, H, spp, 50)
     full = np.zeros((H, W, 3))
-    st = A.oracle_stats()
+    st = O.oracle_stats()
     oracle.oracle_render(sc.desc, C.byref(cam), 0, spp, 1984, 1, 64, 2, full.ctypes.data, C.byref(st))
     assert rays == st.rays
     assert np.allclose(acc, full.astype(np.float32), rtol=1e-6, atol=1e-7)

@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, A, oracle_render
+from conftest import GOLDEN, A, O, oracle_render, oracle_render_region
 from raytracinginoneweekendincuda_b200 import BuiltinScene
 
 ALL_SCENES = list(range(11))
@@ -59,7 +59,7 @@ def test_oracle_matches_live_reference(oracle, ref_stream, earth, sid, W, H, s0,
     cam = sc.camera(W, H, s1, depth)
     img, st = oracle_render(oracle, sc, cam, s0, s1)
     out = np.zeros((H, W, 3))
-    rs = A.ref_stream_stats()
+    rs = O.ref_stream_stats()
     ref_stream.ref_stream_render(sid, W, H, s0, s1, depth, 1984, earth.ctypes.data, earth.shape[1], earth.shape[0], 4,
                                  out.ctypes.data, C.byref(rs))
     assert st.rays == rs.rays and st.draws == rs.draws
@@ -116,3 +116,18 @@ def test_fp32_restating_the_reference_is_not_good_enough(oracle):
     b, _ = oracle_render(oracle, sc, cam, 0, 10, precision=32)
     bad = (np.abs(a - b) > 1e-3 * np.abs(a) + 1e-6).any(axis=2).mean()
     assert bad > 0.005
+
+
+@pytest.mark.parametrize("sid,x0,y0,w,h", [(10, 17, 9, 40, 21), (9, 0, 0, 16, 16), (8, 24, 24, 16, 16), (0, 56, 30, 8, 6)])
+def test_region_render_is_the_crop_of_the_full_render(oracle, earth, sid, x0, y0, w, h):
+    """oracle_render_region keys its streams on the GLOBAL pixel index: a window of the frame is bit-identical to
+    the same pixels of the full render (what the full-size GPU parity tests rely on)."""
+    sc = scene_for(sid, earth)
+    W, H = (64, 36) if sid in (10, 9, 0) else (40, 40)
+    cam = sc.camera(W, H, 3, 50)
+    full, _ = oracle_render(oracle, sc, cam, 1, 3)
+    win, st = oracle_render_region(oracle, sc, cam, x0, y0, w, h, 1, 3)
+    assert np.array_equal(full[y0:y0 + h, x0:x0 + w], win)
+    assert st.paths == w * h * 2
+    out = np.zeros((4, 4, 3))
+    assert oracle.oracle_render_region(sc.desc, C.byref(cam), W - 2, 0, 4, 4, 0, 1, 1984, 1, 64, 1, out.ctypes.data, None) != 0

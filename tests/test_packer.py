@@ -1,0 +1,148 @@
+"""The host packer behind rt_scene_upload (csrc/rt_pack.hpp), through the host-only rt_scene_pack_info:
+hoisting of scene-sized items, stack-depth accounting, validation of malformed input.  No GPU needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import A
+from raytracinginoneweekendincuda_b200 import BuiltinScene
+
+
+def pack(lib, desc, bvh=A.RT_BVH_SAH, flags=0, max_leaf=0):
+    info = A.rt_pack_info()
+    opt = A.rt_upload_options(device=0, bvh=bvh, max_leaf_prims=max_leaf, flags=flags)
+    rc = lib.rt_scene_pack_info(desc, C.byref(opt), C.byref(info))
+    return rc, info
+
+
+def test_ground_sphere_and_mist_are_hoisted(lib, earth):
+    """Book 1 / scene 0: the r = 1000 ground sphere; scene 9: the r = 5000 mist medium (its box contains the whole
+    scene, reference kernel.cu:481-482).  Cornell scenes have no scene-sized item."""
+    for sid, ref_type in [(10, 0), (0, 0), (9, 3)]:
+        sc = BuiltinScene(sid, earth if sid == 9 else None)
+        rc, i = pack(lib, sc.desc)
+        assert rc == 0 and i.n_hoisted == 1
+        assert (i.hoisted[0] >> 31) == 1 and ((i.hoisted[0] >> 29) & 3) == ref_type
+        rc, j = pack(lib, sc.desc, flags=A.RT_UPLOAD_NO_HOIST)
+        assert rc == 0 and j.n_hoisted == 0
+        assert j.n_nodes >= i.n_nodes  # one leaf less in the tree
+        assert (i.n_spheres, i.n_moving, i.n_quads, i.n_media) == (j.n_spheres, j.n_moving, j.n_quads, j.n_media)
+    for sid in (7, 8):
+        sc = BuiltinScene(sid)  # (kept alive: the description belongs to it)
+        rc, i = pack(lib, sc.desc)
+        assert rc == 0 and i.n_hoisted == 0
+
+
+def test_reference_and_list_modes_never_hoist(lib):
+    sc = BuiltinScene(10)
+    for bvh in (A.RT_BVH_REFERENCE, A.RT_BVH_NONE):
+        rc, i = pack(lib, sc.desc, bvh=bvh)
+        assert rc == 0 and i.n_hoisted == 0
+
+
+def test_book1_fits_shared_memory_with_24_warps(lib):
+    """staged scene + traversal stacks + hit queues of 24 warps within the 227 KB a CTA may use."""
+    sc = BuiltinScene(10)
+    rc, i = pack(lib, sc.desc)
+    assert rc == 0
+    assert i.n_materials == 485 and i.n_mat_params > 50  # metals + dielectrics carry an FP64 parameter
+    stack = 768 * 4 * (i.max_depth_bvh + 3)
+    queues = 24 * (64 * 68 + 384)
+    assert i.staged_bytes + stack + queues + 16 <= 232448
+
+
+def _mixed_leaf_scene(n_types):
+    """Coincident primitives of several types: SAH cannot separate them, so they end in ONE mixed leaf, which the
+    packer chains through join nodes (one stack level each)."""
+    prims = (A.rt_prim * 8)()
+    objs = (A.rt_object * 8)()
+    n = 0
+    for rep in range(2):
+        for t in range(n_types):
+            p = prims[n]
+            p.type = [A.RT_PRIM_SPHERE, A.RT_PRIM_MOVING_SPHERE, A.RT_PRIM_QUAD][t]
+            p.material = 0
+            p.a[:] = [0.0, 0.0, 0.0]
+            p.b[:] = [0.0, 0.0, 0.0] if t == 1 else [1.0, 0.0, 0.0]
+            p.c[:] = [0.0, 1.0, 0.0]
+            p.radius = 1.0
+            p.time0, p.time1 = 0.0, 1.0
+            o = objs[n]
+            o.kind = A.RT_OBJ_PRIM
+            o.first_prim, o.prim_count = n, 1
+            o.bbox[:] = [-1, 1, -1, 1, -1, 1]
+            n += 1
+    mats = (A.rt_material * 1)()
+    mats[0].type = A.RT_MAT_LAMBERTIAN
+    mats[0].texture = 0
+    tex = (A.rt_texture * 1)()
+    tex[0].type = A.RT_TEX_SOLID
+    d = A.rt_scene_desc(abi_version=A.RT_ABI_VERSION, n_objects=n, n_prims=n, n_materials=1, n_textures=1,
+                        objects=objs, prims=prims, materials=mats, textures=tex)
+    d._keep = (prims, objs, mats, tex)
+    return d
+
+
+def test_mixed_leaves_count_their_join_levels(lib):
+    """a leaf holding three primitive types becomes two joins above three typed leaves; the stack depth
+    reported to the kernel must include them."""
+    d1 = _mixed_leaf_scene(1)
+    d3 = _mixed_leaf_scene(3)
+    rc1, i1 = pack(lib, C.byref(d1), max_leaf=8, flags=A.RT_UPLOAD_NO_HOIST)  # (coincident = all scene-sized)
+    rc3, i3 = pack(lib, C.byref(d3), max_leaf=8, flags=A.RT_UPLOAD_NO_HOIST)
+    assert rc1 == 0 and rc3 == 0
+    assert i3.max_depth_bvh >= i1.max_depth_bvh + 2
+    assert i3.n_nodes >= 2 + 2 * 2  # root pair + two joins
+
+
+def test_validation_rejects_unknown_enums_and_null_tables(lib):
+    sc = BuiltinScene(9, np.zeros((4, 4, 3), np.uint8))
+    d = sc.desc.contents
+
+    def expect_invalid(mutate, needle):
+        bad = A.rt_scene_desc.from_buffer_copy(d)
+        keep = mutate(bad)
+        rc, _ = pack(lib, C.byref(bad))
+        assert rc == A.RT_ERR_INVALID, needle
+        assert needle in lib.rt_last_error(), lib.rt_last_error()
+        return keep
+
+    def bad_texture(b):
+        t = (A.rt_texture * d.n_textures)(*[d.textures[i] for i in range(d.n_textures)])
+        t[0].type = 7
+        b.textures = t
+        return t
+
+    def bad_material(b):
+        m = (A.rt_material * d.n_materials)(*[d.materials[i] for i in range(d.n_materials)])
+        m[1].type = -1
+        b.materials = m
+        return m
+
+    def bad_object(b):
+        o = (A.rt_object * d.n_objects)(*[d.objects[i] for i in range(d.n_objects)])
+        o[0].kind = 3
+        b.objects = o
+        return o
+
+    def bad_prim(b):
+        p = (A.rt_prim * d.n_prims)(*[d.prims[i] for i in range(d.n_prims)])
+        p[5].type = 9
+        b.prims = p
+        return p
+
+    def null_table(b):
+        b.materials = None
+
+    def negative_count(b):
+        b.n_perlins = -1
+
+    expect_invalid(bad_texture, b"texture type")
+    expect_invalid(bad_material, b"material type")
+    expect_invalid(bad_object, b"object kind")
+    expect_invalid(bad_prim, b"primitive type")
+    expect_invalid(null_table, b"NULL table")
+    expect_invalid(negative_count, b"negative")
+    rc, _ = pack(lib, None)
+    assert rc == A.RT_ERR_INVALID

@@ -17,19 +17,19 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, load_earth_fixture  # noqa: E402
-from raytracinginoneweekendincuda_b200 import _abi as A, _build  # noqa: E402
+from raytracinginoneweekendincuda_b200 import _abi as A  # noqa: E402
+from oracle import bindings as O  # noqa: E402
 
 OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 res = {"gpu": torch.cuda.get_device_name(0), "cpus": os.cpu_count()}
 earth = load_earth_fixture()
-oracle = C.CDLL(_build.oracle_path())
-A.declare_oracle(oracle)
+oracle = O.load_oracle()
 
 
 def oracle_render(sc, cam, s0, s1, seed=1984):
     out = np.zeros((cam.image_height, cam.image_width, 3))
-    st = A.oracle_stats()
+    st = O.oracle_stats()
     oracle.oracle_render(sc.desc, C.byref(cam), s0, s1, seed, 1, 64, os.cpu_count(), out.ctypes.data, C.byref(st))
     return out, st
 
@@ -188,7 +188,7 @@ if "diverge" in what:
         for smp in range(nS):
             cam = sc.camera(W, H, 1, 50)
             want = np.zeros((H, W, 3))
-            st = A.oracle_stats()
+            st = O.oracle_stats()
             oracle.oracle_render(sc.desc, C.byref(cam), smp, smp + 1, 1984, 1, 64, os.cpu_count(), want.ctypes.data, C.byref(st))
             r.render(cam, smp, smp + 1)
             got, _, gst = r.readback()

@@ -4,8 +4,9 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
-from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, _abi as A, _build
-oracle = C.CDLL(_build.oracle_path()); A.declare_oracle(oracle)
+from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, _abi as A
+from oracle import bindings as O
+oracle = O.load_oracle()
 sc = BuiltinScene(10)
 spp = 8
 r = Renderer(sc.desc)
@@ -20,7 +21,7 @@ for W, H in [(480, 270), (960, 540), (1920, 1080), (3840, 2160)]:
     print(W, H, "mean", lin.mean(axis=(0, 1)), "rays/path", st.rays / (W * H * spp), flush=True)
     imgs[("s", W)] = small
 cam = sc.camera(480, 270, spp, 50)
-want = np.zeros((270, 480, 3)); ost = A.oracle_stats()
+want = np.zeros((270, 480, 3)); ost = O.oracle_stats()
 oracle.oracle_render(sc.desc, C.byref(cam), 0, spp, 1984, 1, 64, os.cpu_count(), want.ctypes.data, C.byref(ost))
 want /= spp
 print("oracle 480 mean", want.mean(axis=(0, 1)))

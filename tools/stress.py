@@ -5,8 +5,9 @@ import ctypes as C, os, random, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
-from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, load_earth_fixture, _abi as A, _build
-oracle = C.CDLL(_build.oracle_path()); A.declare_oracle(oracle)
+from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, load_earth_fixture, _abi as A
+from oracle import bindings as O
+oracle = O.load_oracle()
 earth = load_earth_fixture()
 rnd = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
@@ -22,7 +23,7 @@ while time.time() - t0 < budget:
         bvh = A.RT_BVH_SAH  # the linear list over 3400 primitives is slow, not wrong
     sc = scenes[sid]
     cam = sc.camera(W, H, spp + s0, depth)
-    want = np.zeros((H, W, 3)); ost = A.oracle_stats()
+    want = np.zeros((H, W, 3)); ost = O.oracle_stats()
     oracle.oracle_render(sc.desc, C.byref(cam), s0, s0 + spp, 1984, 1, 64, os.cpu_count(), want.ctypes.data, C.byref(ost))
     r = Renderer(sc.desc, bvh=bvh)
     r.render(cam, s0, s0 + spp, variant=variant, block_threads=threads, flags=flags)
