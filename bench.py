@@ -46,6 +46,13 @@ BYTES_NODE = 32.0
 NCU_DRAM_BYTES_4K_LAUNCH = 99915520 + 50284800
 
 
+def earth_texels():
+    """Texels of the reference's earthmap.jpg as its RtwImage produces them: the committed fixture (the bench must
+    not depend on /root/reference; the product decodes the JPEG itself when given a path)."""
+    import numpy as np
+    return np.ascontiguousarray(np.load(os.path.join(ROOT, "tests", "golden", "earthmap_rgb8.npz"))["rgb"])
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -78,8 +85,7 @@ def load_cpu_reference():
     sid = ARGS.scene
     earth = None
     if sid in (2, 9):
-        from raytracinginoneweekendincuda_b200 import load_earth_fixture
-        earth = load_earth_fixture()
+        earth = earth_texels()
     lib, flags = O.load_ref_stream(fast=True), "g++ -O3 -march=native"
     if lib is None:
         lib, flags = O.load_ref_stream(fast=False), "g++ -O2 -ffp-contract=off (the pin build; no -O3 build present)"
@@ -121,8 +127,7 @@ def reference_topology_counts(scene_id=None):
     sid = ARGS.scene if scene_id is None else scene_id
     earth = None
     if sid in (2, 9):
-        from raytracinginoneweekendincuda_b200 import load_earth_fixture
-        earth = load_earth_fixture()
+        earth = earth_texels()
     sc = BuiltinScene(sid, earth)
     W, H = 480, 270
     cam = sc.camera(W, H, 1, WORKLOAD["max_depth"])
@@ -265,7 +270,7 @@ def run_b200_arm():
     import torch
     import torch.distributed as dist
 
-    from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, load_earth_fixture
+    from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer
     from raytracinginoneweekendincuda_b200.multigpu import reduce_accumulators, sample_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -298,7 +303,7 @@ def run_b200_arm():
         torch.cuda.synchronize()
 
     W, H, spp = ARGS.width, ARGS.height, ARGS.spp
-    earth = load_earth_fixture() if ARGS.scene in (2, 9) else None
+    earth = earth_texels() if ARGS.scene in (2, 9) else None
     sc = BuiltinScene(ARGS.scene, earth)  # host scene description (the caller's input)
     cam = sc.camera(W, H, spp, WORKLOAD["max_depth"])
     s0, s1 = sample_range(rank, world, spp)

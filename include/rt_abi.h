@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -182,14 +182,23 @@ enum {
 };
 
 typedef struct rt_upload_options {
-    int32_t device; /* CUDA device ordinal */
+    int32_t device; /* CUDA device ordinal (used when n_devices <= 1) */
     int32_t bvh;    /* RT_BVH_* */
     int32_t max_leaf_prims; /* 0 = default */
     int32_t flags;  /* RT_UPLOAD_* */
+    /* Multi-device, single process (the reference's one launch site, kernel.cu:678-689, fanned out):
+     * n_devices > 1 replicates the packed scene on device_ids[0..n_devices) -- packed ONCE on the host, one copy per
+     * device.  rt_render then gives device k the k-th slice of the sample range on its own stream, and rt_readback
+     * sums the fp32 accumulators on device_ids[0] (one reduction over NVLink) before it resolves the frame. */
+    int32_t n_devices;         /* 0 or 1: single device */
+    int32_t _pad;
+    const int32_t* device_ids; /* NULL: devices 0 .. n_devices-1 */
 } rt_upload_options;
 
 enum {
-    RT_UPLOAD_NO_HOIST = 1 /* keep scene-sized primitives / media inside the BVH (A/B test of the hoisting) */
+    RT_UPLOAD_NO_HOIST = 1, /* keep scene-sized primitives / media inside the BVH (A/B test of the hoisting) */
+    RT_UPLOAD_REDUCE_NCCL = 2 /* multi-device: sum the accumulators with ncclReduce (libnccl.so.2 is dlopen'ed on
+                                 first use) instead of the fused peer-memory reduce + resolve kernel              */
 };
 
 typedef struct rt_render_params {
@@ -233,6 +242,26 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
  * accumulator (row 0 = bottom row, like the reference framebuffer). */
 int rt_render(rt_scene_handle scene, const rt_camera* cam, const rt_render_params* p);
 
+/* Progressive output (replaces the reference's render-then-write-PPM sequence, kernel.cu:681-723, for
+ * long renders): the sample range of `p` is rendered in batches of `batch` samples; after every batch the frame so far
+ * (multi-device: reduced on device 0) is resolved -- mean over the samples done, and gamma + quantise when srgb8 is
+ * wanted -- into one of two pinned host buffers, and `fn` is called with it while the NEXT batch is already
+ * rendering.  The buffers belong to the handle and are valid until the following callback returns. */
+typedef void (*rt_progress_fn)(void* user, const float* linear_rgb, const uint8_t* srgb8, int32_t samples_done,
+                               int32_t samples_total);
+int rt_render_progressive(rt_scene_handle scene, const rt_camera* cam, const rt_render_params* p, int32_t batch,
+                          int32_t want_linear, int32_t want_srgb8, rt_progress_fn fn, void* user);
+
+/* Device-side times of the last rt_render / rt_readback of this handle (CUDA events on each device's stream). */
+typedef struct rt_timing {
+    int32_t n_devices;
+    int32_t _pad;
+    float render_ms[16]; /* per device: its kernel launch(es) of the last rt_render */
+    float reduce_ms;     /* multi-device: the accumulator reduction of the last rt_readback (0 if single) */
+    float resolve_ms;    /* resolve kernel + device-to-host copies of the last rt_readback */
+} rt_timing;
+int rt_get_timing(rt_scene_handle scene, rt_timing* out);
+
 /* Device pointer + float count of the handle's accumulator (for collectives). */
 int rt_accum_ptr(rt_scene_handle scene, float** dev_ptr, uint64_t* n_floats);
 
@@ -259,6 +288,9 @@ typedef struct rt_scene_info {
     int32_t features;      /* RT_FEAT_* bitmask that selected the kernel instantiation */
     int32_t scene_in_smem; /* 1 when nodes+prims+materials are staged in shared memory */
     int32_t variant;       /* RT_VARIANT_* the last rt_render ran (what AUTO resolved to)    */
+    int32_t n_devices;     /* devices the scene is resident on                              */
+    int32_t reduce_path;   /* multi-device: 0 = none yet, 1 = peer-memory fused kernel, 2 = NCCL */
+    int32_t block_threads, registers; /* launch shape and registers/thread of the last rt_render's kernel */
     uint64_t device_bytes;
     int32_t medium_visits[8]; /* T2: reference-topology visit multiplicity per medium_id */
 } rt_scene_info;

@@ -38,6 +38,16 @@ int rt_host_scene_free(rt_host_scene s);
  * n = number of bytes. */
 void rt_image_linearize_rgb8(const uint8_t* srgb, uint8_t* out, uint64_t n);
 
+/* The image half of RtwImage::Load (RtwImage.h:51-87 over stb_image's stbi_loadf, StbImageImpl.cpp:19-21): decodes
+ * a baseline JPEG with stb_image v2.30's arithmetic (integer IDCT, tent-filter chroma upsampling, fixed-point YCbCr:
+ * the texels come out byte for byte as the reference's) into RGB8, row 0 = top.  linearize != 0 applies
+ * rt_image_linearize_rgb8, i.e. returns exactly what RtwImage hands ImageTexture.  Call with rgb_out = NULL to get
+ * the size first.  Progressive JPEG and other formats: RT_ERR_UNSUPPORTED. */
+int rt_image_decode_jpeg(const uint8_t* bytes, uint64_t n_bytes, int32_t* width, int32_t* height, uint8_t* rgb_out,
+                         uint64_t capacity, int32_t linearize);
+/* RtwImage::Load(path): reads the file and decodes + linearises it as above. */
+int rt_image_load(const char* path, int32_t* width, int32_t* height, uint8_t* rgb_out, uint64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,8 +9,8 @@ and a missing or stale library is an error, never a silent fallback.
 from __future__ import annotations
 
 from ._lib import load_library, library_path  # noqa: F401
-from .api import (BuiltinScene, Renderer, SCENE_NAMES, load_earth_fixture, render_scene,  # noqa: F401
+from .api import (BuiltinScene, Renderer, SCENE_NAMES, load_image, render_scene,  # noqa: F401
                   write_ppm)
 
-__all__ = ["load_library", "library_path", "BuiltinScene", "Renderer", "SCENE_NAMES", "load_earth_fixture",
+__all__ = ["load_library", "library_path", "BuiltinScene", "Renderer", "SCENE_NAMES", "load_image",
            "render_scene", "write_ppm"]

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-RT_ABI_VERSION = 1
+RT_ABI_VERSION = 2
 
 RT_OK = 0
 RT_ERR_INVALID = -1
@@ -26,6 +26,7 @@ RT_BVH_SAH, RT_BVH_REFERENCE, RT_BVH_NONE = 0, 1, 2
 RT_FLAG_STATS = 0x100
 RT_FLAG_SCENE_IN_GLOBAL = 0x200
 RT_UPLOAD_NO_HOIST = 1
+RT_UPLOAD_REDUCE_NCCL = 2
 
 D3 = C.c_double * 3
 
@@ -82,7 +83,8 @@ class rt_camera(C.Structure):
 
 
 class rt_upload_options(C.Structure):
-    _fields_ = [("device", C.c_int32), ("bvh", C.c_int32), ("max_leaf_prims", C.c_int32), ("flags", C.c_int32)]
+    _fields_ = [("device", C.c_int32), ("bvh", C.c_int32), ("max_leaf_prims", C.c_int32), ("flags", C.c_int32),
+                ("n_devices", C.c_int32), ("_pad", C.c_int32), ("device_ids", C.POINTER(C.c_int32))]
 
 
 class rt_render_params(C.Structure):
@@ -100,7 +102,18 @@ class rt_stats(C.Structure):
 class rt_scene_info(C.Structure):
     _fields_ = [("n_prims_baked", C.c_int32), ("n_nodes", C.c_int32), ("n_media", C.c_int32),
                 ("max_depth_bvh", C.c_int32), ("features", C.c_int32), ("scene_in_smem", C.c_int32),
-                ("variant", C.c_int32), ("device_bytes", C.c_uint64), ("medium_visits", C.c_int32 * 8)]
+                ("variant", C.c_int32), ("n_devices", C.c_int32), ("reduce_path", C.c_int32),
+                ("block_threads", C.c_int32), ("registers", C.c_int32), ("device_bytes", C.c_uint64),
+                ("medium_visits", C.c_int32 * 8)]
+
+
+class rt_timing(C.Structure):
+    _fields_ = [("n_devices", C.c_int32), ("_pad", C.c_int32), ("render_ms", C.c_float * 16),
+                ("reduce_ms", C.c_float), ("resolve_ms", C.c_float)]
+
+
+# void fn(void* user, const float* linear_rgb, const uint8_t* srgb8, int32 samples_done, int32 samples_total)
+rt_progress_fn = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.c_int32, C.c_int32)
 
 
 class rt_pack_info(C.Structure):
@@ -129,6 +142,11 @@ def declare_host(lib: C.CDLL) -> None:
     lib.rt_host_scene_free.argtypes = [C.c_void_p]
     lib.rt_scene_pack_info.restype = C.c_int
     lib.rt_scene_pack_info.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_upload_options), C.POINTER(rt_pack_info)]
+    lib.rt_image_decode_jpeg.restype = C.c_int
+    lib.rt_image_decode_jpeg.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p,
+                                         C.c_uint64, C.c_int32]
+    lib.rt_image_load.restype = C.c_int
+    lib.rt_image_load.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_uint64]
     lib.rt_image_linearize_rgb8.restype = None
     lib.rt_image_linearize_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
 
@@ -139,6 +157,11 @@ def declare_device(lib: C.CDLL) -> None:
     lib.rt_scene_upload.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_upload_options), C.POINTER(C.c_void_p)]
     lib.rt_render.restype = C.c_int
     lib.rt_render.argtypes = [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_params)]
+    lib.rt_render_progressive.restype = C.c_int
+    lib.rt_render_progressive.argtypes = [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_params), C.c_int32,
+                                          C.c_int32, C.c_int32, rt_progress_fn, C.c_void_p]
+    lib.rt_get_timing.restype = C.c_int
+    lib.rt_get_timing.argtypes = [C.c_void_p, C.POINTER(rt_timing)]
     lib.rt_accum_ptr.restype = C.c_int
     lib.rt_accum_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.rt_sync.restype = C.c_int

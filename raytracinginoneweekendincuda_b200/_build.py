@@ -54,7 +54,7 @@ def build_product(force: bool = False, verbose_ptxas: bool = False, target: str 
         extra += [f"-D{d}" for d in (defines or [])]
         _run(["nvcc", *NVCC_FLAGS, *extra, "-shared",
               os.path.join(CSRC, "rt_device.cu"), os.path.join(CSRC, "rt_host.cpp"),
-              os.path.join(CSRC, "rt_error.cpp"), "-o", target])
+              os.path.join(CSRC, "rt_jpeg.cpp"), os.path.join(CSRC, "rt_error.cpp"), "-o", target])
     if variant:
         return target
     cli = os.path.join(PKG, "rt_cli")

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Optional
+from typing import Callable, Optional, Sequence
 
 import numpy as np
 
@@ -22,7 +22,6 @@ SCENE_NAMES = {
     10: "book1_final",
 }
 
-_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class RtError(RuntimeError):
@@ -34,26 +33,31 @@ def _check(lib, rc: int, what: str) -> None:
         raise RtError(f"{what} failed ({rc}): {lib.rt_last_error().decode(errors='replace')}")
 
 
-def load_earth_fixture() -> Optional[np.ndarray]:
-    """The reference's earthmap texels after RtwImage's linearise+requantise
-    (RtwImage.h:51-105), as committed under tests/golden (made by
-    tests/golden/make_golden.py from the reference's own stb path)."""
-    path = os.path.join(_ROOT, "tests", "golden", "earthmap_rgb8.npz")
-    if not os.path.exists(path):
-        return None
-    return np.ascontiguousarray(np.load(path)["rgb"])
+def load_image(path: str) -> np.ndarray:
+    """RtwImage::Load (reference RtwImage.h:51-87): decodes a baseline JPEG in the host library with stb_image's
+    arithmetic and returns the texels ImageTexture samples -- linearised and re-quantised RGB8, [H, W, 3], row 0 = top."""
+    lib = load_library()
+    w, h = C.c_int32(), C.c_int32()
+    _check(lib, lib.rt_image_load(path.encode(), C.byref(w), C.byref(h), None, 0), "rt_image_load")
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    _check(lib, lib.rt_image_load(path.encode(), C.byref(w), C.byref(h), out.ctypes.data, out.size), "rt_image_load")
+    return out
 
 
 class BuiltinScene:
     """One of the reference's scenes (ids 0..9, kernel.cu:163-172; 10 = Book 1
     final) built on the host into the flat FP64 description."""
 
-    def __init__(self, scene_id: int, earth: Optional[np.ndarray] = None):
+    def __init__(self, scene_id: int, earth=None):
+        """`earth`: the image texture of scenes 2 and 9 -- a path to earthmap.jpg (decoded by the host library), or
+        texels [H, W, 3] uint8 as RtwImage produces them, or None (cyan, Texture.h:113-114)."""
         self.lib = load_library()
         self.scene_id = scene_id
         self._earth = None
         ew = eh = 0
         ptr = None
+        if isinstance(earth, (str, os.PathLike)):
+            earth = load_image(os.fspath(earth))
         if earth is not None:
             self._earth = np.ascontiguousarray(earth, dtype=np.uint8)
             eh, ew = self._earth.shape[0], self._earth.shape[1]
@@ -102,12 +106,20 @@ class BuiltinScene:
 
 
 class Renderer:
-    """A scene resident on one GPU: rt_scene_upload .. rt_scene_free."""
+    """A scene resident on one GPU -- or, with `devices=[...]`, replicated on several GPUs driven by this one
+    process (rt_render splits the sample range over them, rt_readback reduces on the first): rt_scene_upload ..
+    rt_scene_free."""
 
     def __init__(self, desc, device: int = 0, bvh: int = A.RT_BVH_SAH, max_leaf_prims: int = 0,
-                 upload_flags: int = 0):
+                 upload_flags: int = 0, devices: Optional[Sequence[int]] = None):
         self.lib = load_library()
         opt = A.rt_upload_options(device=device, bvh=bvh, max_leaf_prims=max_leaf_prims, flags=upload_flags)
+        self._ids = None
+        if devices is not None and len(devices) > 0:
+            self._ids = (C.c_int32 * len(devices))(*devices)
+            opt.n_devices = len(devices)
+            opt.device_ids = self._ids
+            device = devices[0]
         self._h = C.c_void_p()
         _check(self.lib, self.lib.rt_scene_upload(desc, C.byref(opt), C.byref(self._h)), "rt_scene_upload")
         self.device = device
@@ -123,6 +135,32 @@ class Renderer:
                                flags=flags, stream=stream or None, accum=accum_ptr or None)
         self._cam = cam
         _check(self.lib, self.lib.rt_render(self._h, C.byref(cam), C.byref(p)), "rt_render")
+
+    def render_progressive(self, cam: A.rt_camera, batch: int, on_frame: Callable, sample_begin: int = 0,
+                           sample_end: Optional[int] = None, seed: int = 1984, linear: bool = False,
+                           srgb8: bool = True, variant: int = A.RT_VARIANT_AUTO) -> None:
+        """Renders [sample_begin, sample_end) in batches; after each batch `on_frame(linear|None, srgb8|None,
+        samples_done, samples_total)` gets the frame so far (numpy views of the handle's pinned buffers, valid
+        during the call) while the next batch renders."""
+        if sample_end is None:
+            sample_end = cam.samples_per_pixel
+        H, W = cam.image_height, cam.image_width
+
+        def trampoline(_user, lin, s8, done, total):
+            a = np.ctypeslib.as_array(lin, shape=(H, W, 3)) if lin else None
+            b = np.ctypeslib.as_array(s8, shape=(H, W, 3)) if s8 else None
+            on_frame(a, b, done, total)
+
+        cb = A.rt_progress_fn(trampoline)
+        p = A.rt_render_params(sample_begin=sample_begin, sample_end=sample_end, seed=seed, variant=variant, clear=1)
+        self._cam = cam
+        _check(self.lib, self.lib.rt_render_progressive(self._h, C.byref(cam), C.byref(p), batch, 1 if linear else 0,
+                                                        1 if srgb8 else 0, cb, None), "rt_render_progressive")
+
+    def timing(self) -> A.rt_timing:
+        t = A.rt_timing()
+        _check(self.lib, self.lib.rt_get_timing(self._h, C.byref(t)), "rt_get_timing")
+        return t
 
     def sync(self) -> None:
         _check(self.lib, self.lib.rt_sync(self._h), "rt_sync")
@@ -162,10 +200,8 @@ class Renderer:
 
 
 def render_scene(scene_id: int, width: int, height: int, spp: int, max_depth: int = 50, seed: int = 1984,
-                 device: int = 0, bvh: int = A.RT_BVH_SAH, earth: Optional[np.ndarray] = None, flags: int = 0):
-    """Convenience: build, upload, render, read back.  Returns (linear, stats)."""
-    if earth is None and scene_id in (2, 9):
-        earth = load_earth_fixture()
+                 device: int = 0, bvh: int = A.RT_BVH_SAH, earth=None, flags: int = 0):
+    """Convenience: build, upload, render, read back.  Returns (linear, stats).  `earth`: see BuiltinScene."""
     sc = BuiltinScene(scene_id, earth)
     cam = sc.camera(width, height, spp, max_depth)
     r = Renderer(sc.desc, device=device, bvh=bvh)

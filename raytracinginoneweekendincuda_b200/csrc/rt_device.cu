@@ -1,13 +1,23 @@
-// rt_device.cu -- kernels and the device half of the C ABI (include/rt_abi.h).
+// rt_device.cu -- the device half of the C ABI (include/rt_abi.h): scene arena upload, launch configuration,
+// multi-device fan-out, accumulator reduction, resolve + readback, progressive output.
 //
-// Replaces the reference's RenderInit + Render launches and the device-side
-// object graph they walk (reference kernel.cu:110-154, launched :681-689).
+// Replaces the reference's RenderInit + Render launches and the host reads of its managed framebuffer
+// (reference kernel.cu:110-154, launched :676-691, read :696-723).  The render kernels live in rt_kernels.cuh /
+// rt_kernel_hq.cuh.  No CPU fallback: without a CUDA device every entry point returns an error.
 //
-// The kernels live in rt_kernels.cuh / rt_kernel_hq.cuh; this file is the host side: arena upload, launch
-// configuration, resolve + readback, multi-device fan-out.
-// No CPU fallback: without a CUDA device every entry point returns an error.
+// Multi-device: ONE host process drives N devices.  The scene is packed once and its arena -- one
+// position-independent block -- is copied to every device; rt_render gives device k the k-th slice of the sample
+// range on that device's own stream (the random stream is keyed on the global sample index, so the union is the
+// 1-device sample set); rt_readback sums the fp32 accumulators on device 0 and resolves the frame there:
+//   * peer path (default where every device can map device 0's peers -- NVLink / NVSwitch): ReduceResolveKernel
+//     reads the N accumulators straight from peer memory, sums them in device order (deterministic), and applies
+//     mean / gamma / quantise / row flip in the same pass -- collective and epilogue are one kernel, no staging copy;
+//   * NCCL path (RT_UPLOAD_REDUCE_NCCL, or no peer access): one ncclReduce to device 0, then the same kernel.
+//     libnccl.so.2 is dlopen'ed on first use, so single-device hosts carry no NCCL dependency.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -37,27 +47,83 @@ namespace {
 
 using namespace rtdev;
 
-// kernel.cu:147-153 (mean, sqrt gamma) + :712-718 (clamp to [0,0.999], *256),
-// fused with the row flip to PPM order (kernel.cu:699: top row first).
-__global__ void ResolveKernel(const float* __restrict__ accum, float* __restrict__ linearOut, uint8_t* __restrict__ srgbOut,
-                              int width, int height, float invSpp)
-{
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = width * height;
-    if (idx >= n) return;
-    const float r = accum[idx * 3 + 0] * invSpp, g = accum[idx * 3 + 1] * invSpp, b = accum[idx * 3 + 2] * invSpp;
-    if (linearOut) {
-        linearOut[idx * 3 + 0] = r;
-        linearOut[idx * 3 + 1] = g;
-        linearOut[idx * 3 + 2] = b;
+constexpr int kMaxDevices = 16;
+
+// Every entry point selects the device it works on and puts the caller's current device back on the way out: a
+// host that drives several GPUs itself (torch, a multi-device C++ application) must not find it changed.
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { cudaGetDevice(&saved); }
+    ~DeviceGuard()
+    {
+        if (saved >= 0) cudaSetDevice(saved);
     }
-    if (srgbOut) {
-        const int i = idx % width, j = idx / width;
-        const int o = ((height - 1 - j) * width + i) * 3;
-        const float c[3] = {sqrtf(r), sqrtf(g), sqrtf(b)};
-        for (int k = 0; k < 3; ++k) {
-            const float v = c[k] < 0.0f ? 0.0f : (c[k] > 0.999f ? 0.999f : c[k]);
-            srgbOut[o + k] = (uint8_t)(int)(256.0f * v);
+};
+
+// ------------------------------------------------------------------ output
+// Reduce + resolve in one pass (reference kernel.cu:147-153: mean, sqrt gamma; :712-718: clamp to [0,0.999], *256;
+// :699: top row first).  `set` holds the fp32 accumulators of the participating devices -- device 0's own and, on
+// the peer path, the others' mapped over NVLink: they are summed in device order, so the N-device frame differs
+// from the 1-device frame by fp32 summation order only, and is the same from run to run.  The sum is written back
+// to device 0's accumulator when several were read (what a reduce leaves there).  Each thread moves VEC
+// consecutive floats: 128-bit loads and stores on the accumulators and the linear output, a 32-bit store of four
+// quantised bytes when a row is a multiple of four floats.
+struct AccumSet {
+    const float* p[kMaxDevices];
+    int n;
+};
+
+template <int VEC>
+__global__ void ReduceResolveKernel(const AccumSet set, float* __restrict__ sumOut, float* __restrict__ linearOut,
+                                    uint8_t* __restrict__ srgbOut, int width, int height, float invSpp)
+{
+    const long long nFloats = (long long)width * height * 3;
+    const long long first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (first >= nFloats) return;
+    float v[VEC];
+    if (VEC == 4 && first + 4 <= nFloats) {
+        float4 a = *reinterpret_cast<const float4*>(set.p[0] + first);
+        for (int k = 1; k < set.n; ++k) {
+            const float4 b = *reinterpret_cast<const float4*>(set.p[k] + first);
+            a.x += b.x;
+            a.y += b.y;
+            a.z += b.z;
+            a.w += b.w;
+        }
+        if (sumOut) *reinterpret_cast<float4*>(sumOut + first) = a;
+        v[0] = a.x * invSpp;
+        v[1 % VEC] = a.y * invSpp;
+        v[2 % VEC] = a.z * invSpp;
+        v[3 % VEC] = a.w * invSpp;
+        if (linearOut) *reinterpret_cast<float4*>(linearOut + first) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+    } else {
+        for (int e = 0; e < VEC; ++e) {
+            if (first + e >= nFloats) break;
+            float a = set.p[0][first + e];
+            for (int k = 1; k < set.n; ++k) a += set.p[k][first + e];
+            if (sumOut) sumOut[first + e] = a;
+            v[e] = a * invSpp;
+            if (linearOut) linearOut[first + e] = v[e];
+        }
+    }
+    if (!srgbOut) return;
+    const long long rowLen = (long long)width * 3;
+    uint8_t q[VEC];
+    for (int e = 0; e < VEC; ++e) {
+        float g = sqrtf(v[e]);
+        g = g < 0.0f ? 0.0f : (g > 0.999f ? 0.999f : g);
+        q[e] = (uint8_t)(int)(256.0f * g);
+    }
+    const long long row = first / rowLen;
+    if (VEC == 4 && (rowLen & 3) == 0 && first + 4 <= nFloats) {
+        const long long o = (height - 1 - row) * rowLen + (first - row * rowLen);
+        *reinterpret_cast<uchar4*>(srgbOut + o) = make_uchar4(q[0], q[1 % VEC], q[2 % VEC], q[3 % VEC]);
+    } else {
+        for (int e = 0; e < VEC; ++e) {
+            const long long f = first + e;
+            if (f >= nFloats) break;
+            const long long r = f / rowLen;
+            srgbOut[(height - 1 - r) * rowLen + (f - r * rowLen)] = q[e];
         }
     }
 }
@@ -83,6 +149,7 @@ __global__ void FmaPeakKernel(float* out, int iters)
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+
 
 using KernelFn = void (*)(const DevScene, const DevCamera, const RenderArgs);
 
@@ -124,48 +191,91 @@ KernelFn PickKernelForFeatures(int features, int variant, bool smem, bool stats,
     return PickKernel<kFeatAll>(variant, smem, stats);
 }
 
-// Frame-sized device buffers (accumulator, readback staging) are recycled across
-// handles: cudaMalloc/cudaFree of ~100 MB blocks was measured at up to 0.5 s per
-// upload/free cycle, which is what an application rendering frame after frame does.
+// Frame-sized device buffers (accumulator, readback staging) and scene arenas are recycled across handles:
+// cudaMalloc/cudaFree of ~100 MB blocks was measured at up to 0.5 s per upload/free cycle, which is what an
+// application rendering frame after frame does.  The cache is stream-ordered: a block is parked together with an
+// event recorded on the stream that last used it, and whoever takes it makes its own stream wait for that event,
+// so a block is never handed to new work while old work on another stream still touches it.  When the cache is
+// full the oldest block is returned to the driver.
 struct BigBlock {
     int device;
     size_t bytes;
     void* ptr;
+    cudaEvent_t idle; // may be nullptr (block known to be idle)
 };
 std::mutex gBigMutex;
 std::vector<BigBlock> gBigCache;
 constexpr size_t kBigCacheEntries = 8;
 
-cudaError_t BigMalloc(int device, void** out, size_t bytes)
+// The caller has made `device` current.
+cudaError_t BigMalloc(int device, void** out, size_t bytes, cudaStream_t stream)
 {
+    BigBlock got{};
+    bool found = false;
     {
         std::lock_guard<std::mutex> lock(gBigMutex);
         for (size_t k = 0; k < gBigCache.size(); ++k)
             if (gBigCache[k].device == device && gBigCache[k].bytes == bytes) {
-                *out = gBigCache[k].ptr;
+                got = gBigCache[k];
                 gBigCache.erase(gBigCache.begin() + (long)k);
-                return cudaSuccess;
+                found = true;
+                break;
             }
+    }
+    if (found) {
+        if (got.idle) {
+            const cudaError_t e = cudaStreamWaitEvent(stream, got.idle, 0);
+            cudaEventDestroy(got.idle);
+            if (e != cudaSuccess) {
+                cudaFree(got.ptr);
+                return e;
+            }
+        }
+        *out = got.ptr;
+        return cudaSuccess;
     }
     return cudaMalloc(out, bytes);
 }
 
-void BigFree(int device, void* ptr, size_t bytes)
+// The caller has made `device` current; `stream` is the stream that last used the block.
+void BigFree(int device, void* ptr, size_t bytes, cudaStream_t stream)
 {
     if (!ptr) return;
+    BigBlock blk{device, bytes, ptr, nullptr};
+    if (cudaEventCreateWithFlags(&blk.idle, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(blk.idle, stream) != cudaSuccess) {
+        if (blk.idle) cudaEventDestroy(blk.idle);
+        cudaStreamSynchronize(stream);
+        cudaFree(ptr);
+        return;
+    }
+    BigBlock evicted{};
+    bool evict = false;
     {
         std::lock_guard<std::mutex> lock(gBigMutex);
-        if (gBigCache.size() < kBigCacheEntries) {
-            gBigCache.push_back(BigBlock{device, bytes, ptr});
-            return;
+        if (gBigCache.size() >= kBigCacheEntries) {
+            evicted = gBigCache.front();
+            gBigCache.erase(gBigCache.begin());
+            evict = true;
         }
+        gBigCache.push_back(blk);
     }
-    cudaFree(ptr);
+    if (evict) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cudaSetDevice(evicted.device) == cudaSuccess) {
+            if (evicted.idle) {
+                cudaEventSynchronize(evicted.idle);
+                cudaEventDestroy(evicted.idle);
+            }
+            cudaFree(evicted.ptr);
+        }
+        if (cur >= 0) cudaSetDevice(cur);
+    }
 }
 
-// Host image of the device arena: every table of the scene back to back, 256-byte
-// aligned, so that one allocation and ONE host-to-device copy upload the scene
-// (and one ncclBroadcast would replicate it).
+// Host image of the device arena: every table of the scene back to back, 256-byte aligned and free of absolute
+// addresses (image texels are referenced by offset), so that one allocation and ONE host-to-device copy upload the
+// scene, and the same bytes serve every device.
 struct ArenaBuilder {
     std::vector<char> bytes;
     template <class T> size_t Add(const std::vector<T>& v)
@@ -185,43 +295,61 @@ struct ArenaBuilder {
     }
 };
 
-} // namespace
-
-struct rt_scene_s {
-    int device = 0;
-    DevScene dev{};
-    rtpack::Packed* host = nullptr; // kept for sizes / info
-    char* arena = nullptr; // one device block: scene tables, images, counters, debug records
-    size_t arenaBytes = 0;
-    uint64_t deviceBytes = 0;
-    bool fitsSmem = false;
-    uint32_t stagedBytes = 0;
-    int smCount = 0;
-    int maxSmemOptin = 0;
-    // accumulator + counters
-    float* accum = nullptr;
-    size_t accumFloats = 0;
-    float* linearStage = nullptr;
-    uint8_t* srgbStage = nullptr;
-    size_t linearStageFloats = 0, srgbStageBytes = 0;
-    unsigned long long* stats = nullptr;
-    unsigned int* tileCounter = nullptr;
-    float* debugOut = nullptr; // test hook, 256*8 floats
-    int debugPixel = -1, debugSample = -1;
-    cudaStream_t lastStream = nullptr;
-    rt_camera lastCam{};
-    bool rendered = false;
-    int pickedFeatures = 0;
-    int pickedVariant = 0;
+// ------------------------------------------------------------------- NCCL
+// The five NCCL entry points the reduce path uses, resolved from libnccl.so.2 at first use (if the host process has
+// already loaded an NCCL -- torch does -- dlopen hands back that one).  Types are spelled out here so that neither the
+// build nor single-device hosts need NCCL headers or libraries.
+typedef struct ncclComm* NcclComm;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(NcclComm*, int, const int*) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
 };
+constexpr int kNcclFloat32 = 7, kNcclSum = 0; // ncclFloat32, ncclSum (nccl.h: ncclDataType_t, ncclRedOp_t)
+std::mutex gNcclMutex;
+NcclApi gNccl;
 
-extern "C" {
+bool LoadNccl()
+{
+    std::lock_guard<std::mutex> lock(gNcclMutex);
+    if (gNccl.ok) return true;
+    if (!gNccl.lib) gNccl.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!gNccl.lib) gNccl.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!gNccl.lib) {
+        rt_set_error("multi-device reduce: cannot load libnccl.so.2 (%s)", dlerror());
+        return false;
+    }
+    auto sym = [&](const char* name) { return dlsym(gNccl.lib, name); };
+    gNccl.CommInitAll = reinterpret_cast<int (*)(NcclComm*, int, const int*)>(sym("ncclCommInitAll"));
+    gNccl.CommDestroy = reinterpret_cast<int (*)(NcclComm)>(sym("ncclCommDestroy"));
+    gNccl.Reduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, int, NcclComm, cudaStream_t)>(sym("ncclReduce"));
+    gNccl.GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+    gNccl.GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
+    gNccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
+    gNccl.ok = gNccl.CommInitAll && gNccl.CommDestroy && gNccl.Reduce && gNccl.GroupStart && gNccl.GroupEnd && gNccl.GetErrorString;
+    if (!gNccl.ok) rt_set_error("multi-device reduce: libnccl.so.2 lacks an expected entry point");
+    return gNccl.ok;
+}
 
-static uint32_t Pad16(size_t b) { return (uint32_t)((b + 15) / 16 * 16); }
+#define RT_NCCL(call)                                                                                   \
+    do {                                                                                                \
+        const int r_ = (call);                                                                          \
+        if (r_ != 0) {                                                                                  \
+            rt_set_error("%s failed: %s (%s:%d)", #call, gNccl.GetErrorString(r_), __FILE__, __LINE__); \
+            return RT_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+
+uint32_t Pad16(size_t b) { return (uint32_t)((b + 15) / 16 * 16); }
 
 // Bytes a CTA stages in shared memory: every table SetupScene<true> copies, each padded to 16 (an empty table
 // still holds one zeroed record).
-static uint32_t StagedBytes(const rtpack::Packed& pk)
+uint32_t StagedBytes(const rtpack::Packed& pk)
 {
     return Pad16(std::max<size_t>(1, pk.nodes.size()) * sizeof(DevNode)) +
            Pad16(std::max<size_t>(1, pk.spheres.size()) * sizeof(DevSphere)) +
@@ -232,6 +360,322 @@ static uint32_t StagedBytes(const rtpack::Packed& pk)
            Pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial)) +
            Pad16(std::max<size_t>(1, pk.mat_params.size()) * sizeof(double));
 }
+
+
+// One device's share of a handle.
+struct DeviceCtx {
+    int device = 0;
+    DevScene dev{};
+    char* arena = nullptr; // one device block: scene tables, images, counters, debug records
+    float* accum = nullptr;
+    size_t accumFloats = 0;
+    unsigned long long* stats = nullptr; // [0] rays [1] paths [2] node tests [3] prim tests
+    unsigned int* tileCounter = nullptr;
+    float* debugOut = nullptr; // test hook, 256*8 floats
+    cudaStream_t ownStream = nullptr;  // multi-device handles: this device's stream
+    cudaStream_t lastStream = nullptr; // the stream the last render ran on
+    cudaEvent_t evStart = nullptr, evStop = nullptr; // around the render launch(es)
+    int smCount = 0, maxSmemOptin = 0;
+    int sampleBegin = 0, sampleEnd = 0; // slice of the last render
+};
+
+} // namespace
+
+struct rt_scene_s {
+    std::vector<DeviceCtx> devs;
+    rtpack::Packed* host = nullptr; // kept for sizes / info
+    size_t arenaBytes = 0;
+    uint32_t stagedBytes = 0;
+    int uploadFlags = 0;
+    // multi-device
+    int reducePath = 0;      // 0 none, 1 peer-memory fused kernel, 2 NCCL
+    bool peerCapable = false;
+    std::vector<NcclComm> comms;
+    // output staging on device 0: two sets (progressive output double-buffers them)
+    float* linearStage[2] = {nullptr, nullptr};
+    uint8_t* srgbStage[2] = {nullptr, nullptr};
+    size_t linearStageFloats[2] = {0, 0}, srgbStageBytes[2] = {0, 0};
+    float* hostLinear[2] = {nullptr, nullptr}; // pinned, progressive output
+    uint8_t* hostSrgb[2] = {nullptr, nullptr};
+    size_t hostLinearFloats = 0, hostSrgbBytes = 0;
+    cudaStream_t copyStream = nullptr; // device 0: progressive device-to-host copies
+    cudaEvent_t evReduce0 = nullptr, evReduce1 = nullptr, evResolve1 = nullptr;
+    bool timedReadback = false;
+    int debugPixel = -1, debugSample = -1;
+    rt_camera lastCam{};
+    bool rendered = false;
+    bool fitsSmem = false;
+    int pickedFeatures = 0, pickedVariant = 0, pickedThreads = 0, pickedRegisters = 0;
+};
+
+namespace {
+
+void FreeDevice(rt_scene_s* h, DeviceCtx& d)
+{
+    if (cudaSetDevice(d.device) != cudaSuccess) return;
+    cudaStream_t s = d.lastStream ? d.lastStream : d.ownStream;
+    if (h->rendered) cudaStreamSynchronize(s);
+    BigFree(d.device, d.arena, h->arenaBytes, s);
+    BigFree(d.device, d.accum, d.accumFloats * sizeof(float), s);
+    if (d.evStart) cudaEventDestroy(d.evStart);
+    if (d.evStop) cudaEventDestroy(d.evStop);
+    if (d.ownStream) cudaStreamDestroy(d.ownStream);
+    d = DeviceCtx{};
+}
+
+// Output stage buffers on device 0 (the caller has made it current).
+int EnsureStage(rt_scene_s* h, int set, size_t nFloats, bool linear, bool srgb, cudaStream_t stream)
+{
+    DeviceCtx& d0 = h->devs[0];
+    if (linear && h->linearStageFloats[set] < nFloats) {
+        BigFree(d0.device, h->linearStage[set], h->linearStageFloats[set] * sizeof(float), stream);
+        h->linearStage[set] = nullptr;
+        h->linearStageFloats[set] = 0;
+        RT_CUDA(BigMalloc(d0.device, reinterpret_cast<void**>(&h->linearStage[set]), nFloats * sizeof(float), stream));
+        h->linearStageFloats[set] = nFloats;
+    }
+    if (srgb && h->srgbStageBytes[set] < nFloats) {
+        BigFree(d0.device, h->srgbStage[set], h->srgbStageBytes[set], stream);
+        h->srgbStage[set] = nullptr;
+        h->srgbStageBytes[set] = 0;
+        RT_CUDA(BigMalloc(d0.device, reinterpret_cast<void**>(&h->srgbStage[set]), nFloats, stream));
+        h->srgbStageBytes[set] = nFloats;
+    }
+    return RT_OK;
+}
+
+// Queues, on device 0's stream: [multi-device: the reduction of all accumulators onto device 0] + the resolve of the
+// frame into stage set `set`.  `src` = a caller-owned accumulator (single device) or nullptr.  Leaves device 0 current.
+int QueueReduceResolve(rt_scene_s* h, const float* src, int set, bool linear, bool srgb, float invSpp)
+{
+    const int nDev = (int)h->devs.size();
+    DeviceCtx& d0 = h->devs[0];
+    const int W = h->lastCam.image_width, H = h->lastCam.image_height;
+    const size_t nFloats = (size_t)W * H * 3;
+    RT_CUDA(cudaSetDevice(d0.device));
+    cudaStream_t s0 = d0.lastStream;
+    AccumSet acc{};
+    acc.n = 1;
+    acc.p[0] = src ? src : d0.accum;
+    float* sumOut = nullptr;
+    const bool multi = nDev > 1 && !src;
+    if (h->timedReadback) RT_CUDA(cudaEventRecord(h->evReduce0, s0));
+    if (multi) {
+        // device 0's stream waits for every device's render
+        for (int k = 1; k < nDev; ++k) RT_CUDA(cudaStreamWaitEvent(s0, h->devs[k].evStop, 0));
+        if (h->reducePath == 0) h->reducePath = (h->peerCapable && !(h->uploadFlags & RT_UPLOAD_REDUCE_NCCL)) ? 1 : 2;
+        if (h->reducePath == 1) {
+            acc.n = nDev;
+            for (int k = 1; k < nDev; ++k) acc.p[k] = h->devs[k].accum; // peer-mapped: read over NVLink by the kernel
+            sumOut = d0.accum;
+        } else {
+            if (!LoadNccl()) return RT_ERR_UNSUPPORTED;
+            if (h->comms.empty()) {
+                std::vector<int> ids;
+                for (const DeviceCtx& d : h->devs) ids.push_back(d.device);
+                h->comms.assign((size_t)nDev, nullptr);
+                RT_NCCL(gNccl.CommInitAll(h->comms.data(), nDev, ids.data()));
+            }
+            // every rank's collective runs on that device's render stream, after its kernel
+            RT_NCCL(gNccl.GroupStart());
+            for (int k = 0; k < nDev; ++k) {
+                DeviceCtx& d = h->devs[k];
+                RT_CUDA(cudaSetDevice(d.device));
+                RT_NCCL(gNccl.Reduce(d.accum, k == 0 ? d.accum : nullptr, nFloats, kNcclFloat32, kNcclSum, 0, h->comms[(size_t)k],
+                                     d.lastStream));
+            }
+            RT_NCCL(gNccl.GroupEnd());
+            RT_CUDA(cudaSetDevice(d0.device));
+        }
+    }
+    if (h->timedReadback && h->reducePath == 2) RT_CUDA(cudaEventRecord(h->evReduce1, s0));
+    if (linear || srgb || sumOut) {
+        const int rc = EnsureStage(h, set, nFloats, linear, srgb, s0);
+        if (rc != RT_OK) return rc;
+        float* lin = linear ? h->linearStage[set] : nullptr;
+        uint8_t* s8 = srgb ? h->srgbStage[set] : nullptr;
+        bool aligned = (reinterpret_cast<uintptr_t>(lin) & 15u) == 0;
+        for (int k = 0; k < acc.n; ++k) aligned = aligned && (reinterpret_cast<uintptr_t>(acc.p[k]) & 15u) == 0;
+        if (aligned) {
+            const long long threads = ((long long)nFloats + 3) / 4;
+            ReduceResolveKernel<4><<<(unsigned)((threads + 255) / 256), 256, 0, s0>>>(acc, sumOut, lin, s8, W, H, invSpp);
+        } else {
+            ReduceResolveKernel<1><<<(unsigned)((nFloats + 255) / 256), 256, 0, s0>>>(acc, sumOut, lin, s8, W, H, invSpp);
+        }
+        RT_CUDA(cudaGetLastError());
+    }
+    if (h->timedReadback && h->reducePath != 2) RT_CUDA(cudaEventRecord(h->evReduce1, s0));
+    if (multi) {
+        // device 0 now holds the total: the partial sums of the others are spent.  Clearing them (after the reduce has
+        // read them) keeps "render more samples, reduce again" correct.
+        cudaEvent_t reduced = h->devs[0].evStop; // re-recorded: the next render records it again before anyone waits
+        RT_CUDA(cudaEventRecord(reduced, s0));
+        for (int k = 1; k < nDev; ++k) {
+            DeviceCtx& d = h->devs[k];
+            RT_CUDA(cudaSetDevice(d.device));
+            RT_CUDA(cudaStreamWaitEvent(d.lastStream, reduced, 0));
+            RT_CUDA(cudaMemsetAsync(d.accum, 0, nFloats * sizeof(float), d.lastStream));
+        }
+        RT_CUDA(cudaSetDevice(d0.device));
+    }
+    return RT_OK;
+}
+
+// Launch configuration + launch of samples [begin, end) on one device (made current by the caller).
+int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_params* p, int begin, int end, float* accum,
+             cudaStream_t stream, bool clear)
+{
+    const size_t nFloats = (size_t)cam->image_width * cam->image_height * 3;
+    if (clear) {
+        RT_CUDA(cudaMemsetAsync(accum, 0, nFloats * sizeof(float), stream));
+        RT_CUDA(cudaMemsetAsync(d.stats, 0, 4 * sizeof(unsigned long long), stream));
+    }
+    RT_CUDA(cudaMemsetAsync(d.tileCounter, 0, sizeof(unsigned int), stream));
+
+    int variant = p->variant;
+    if (variant == RT_VARIANT_AUTO)
+        variant = (long long)end - begin <= RT_HT_MAX_SAMPLES ? RT_VARIANT_HITQUEUE : RT_VARIANT_MEGAKERNEL;
+    const bool wave = variant == RT_VARIANT_WAVEFRONT;
+    const bool hitQueue = variant == RT_VARIANT_HITQUEUE;
+    const bool queued = variant == RT_VARIANT_HEADTAIL || hitQueue; // the two queue kernels share their launch shape
+
+    const DevCamera dc = rtpack::MakeCamera(*cam);
+    RenderArgs a{};
+    a.accum = accum;
+    a.stats = d.stats;
+    a.tileCounter = d.tileCounter;
+    a.sampleBegin = begin;
+    a.sampleEnd = end;
+    a.seed = p->seed;
+    a.debugPixel = h->debugPixel;
+    a.debugSample = h->debugSample;
+    a.debugOut = h->debugPixel >= 0 ? d.debugOut : nullptr;
+    // leaf turn every 2nd step (measured best: 1 -> 11.3, 2 -> 11.5, 4 -> 11.2 Grays/s in round 1; again in round 2);
+    // development knob in flags bits 4-5: 1 = every step, 2 = every 4th, 3 = every 8th
+    static const int kLeafMasks[4] = {1, 0, 3, 7};
+    a.megaLeafMask = kLeafMasks[(p->flags >> 4) & 3];
+    // tuning knobs of the wavefront variant (development): flags bits 12-15 slots/32, 16-20 idle-exit, 21-25 leaf
+    // batch, 26-30 refill minimum
+    int waveSlots = ((p->flags >> 12) & 0xf) * 32;
+    a.waveIdleExit = (p->flags >> 16) & 0x1f;
+    a.waveLeafBatch = (p->flags >> 21) & 0x1f;
+    a.waveRefillMin = (p->flags >> 26) & 0x1f;
+    if (a.waveIdleExit <= 0) a.waveIdleExit = 16;
+    if (a.waveLeafBatch <= 0) a.waveLeafBatch = 16;
+    if (a.waveRefillMin <= 0) a.waveRefillMin = 8;
+    const rtpack::Packed& pk = *h->host;
+    a.nodesBytes = Pad16(std::max<size_t>(1, pk.nodes.size()) * sizeof(DevNode));
+    a.spheresBytes = Pad16(std::max<size_t>(1, pk.spheres.size()) * sizeof(DevSphere));
+    a.sphereMatBytes = Pad16(std::max<size_t>(1, pk.sphere_material.size()) * sizeof(int32_t));
+    a.movingBytes = Pad16(std::max<size_t>(1, pk.moving.size()) * sizeof(DevMovingSphere));
+    a.quadsBytes = Pad16(std::max<size_t>(1, pk.quads.size()) * sizeof(DevQuad));
+    a.mediaBytes = Pad16(std::max<size_t>(1, pk.media.size()) * sizeof(DevMedium));
+    a.materialsBytes = Pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial));
+    a.matParamsBytes = Pad16(std::max<size_t>(1, pk.mat_params.size()) * sizeof(double));
+
+    const int featClass = d.dev.features == 0 ? kFeatSpheres : ((d.dev.features & ~kFeatMotion) == 0 ? kFeatMotion : kFeatAll);
+    const int maxThreads = wave ? 512 : (queued ? HtMaxThreads(featClass) : MegaMaxThreads(featClass));
+    int threads = p->block_threads > 0 ? p->block_threads : maxThreads;
+    threads = std::max(32, std::min(maxThreads, (threads / 32) * 32));
+    int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;
+    const int stackLevels = std::max(3, std::min(kMaxStackLevels, h->host->max_depth + 3)); // + sentinel slot
+    a.stackLevels = stackLevels;
+    if (wave) blocksPerSm = 1;
+    const size_t warpBytes = hitQueue ? HqWarpBytes(featClass) : HtWarpBytes(featClass);
+    if (queued && p->block_threads <= 0 && !(p->flags & RT_FLAG_SCENE_IN_GLOBAL)) {
+        // the largest block whose stacks + queues still leave room for the scene in shared memory
+        // (if none does, the scene stays in global memory and the block is as large as registers allow)
+        threads = maxThreads;
+        for (int cand = maxThreads; cand >= 384; cand -= 64)
+            if ((size_t)cand * 4 * stackLevels + (size_t)(cand / 32) * warpBytes + 16 + h->stagedBytes <= (size_t)d.maxSmemOptin) {
+                threads = cand;
+                break;
+            }
+    }
+    const size_t stackBytes = (size_t)threads * 4 * stackLevels;
+    size_t poolBytes = queued ? (size_t)(threads / 32) * warpBytes + 16 : 0;
+    if (wave) {
+        // 64 slots (an 8x8 tile) measured best: 96 or 128 fill SHADE/GEN chunks better but cost more shared
+        // memory traffic and longer tile tails (profiles/r1_wavefront_parameter_sweep.json)
+        if (waveSlots < 64 || waveSlots > 128) waveSlots = 64;
+        poolBytes = (size_t)(threads / 32) * PoolBytes(waveSlots) + 16;
+    }
+    a.waveSlots = waveSlots;
+    const int tileH = wave ? waveSlots / 8 : kTileH;
+    a.tilesX = (cam->image_width + kTileW - 1) / kTileW;
+    a.tilesY = (cam->image_height + tileH - 1) / tileH;
+    const bool wantStats = (p->flags & RT_FLAG_STATS) != 0 || a.debugOut != nullptr;
+    const bool smem = !(p->flags & RT_FLAG_SCENE_IN_GLOBAL) &&
+                      stackBytes + poolBytes + h->stagedBytes <= (size_t)d.maxSmemOptin / (size_t)blocksPerSm;
+    const size_t smemBytes = stackBytes + poolBytes + (smem ? h->stagedBytes : 0);
+    if (smemBytes > (size_t)d.maxSmemOptin) {
+        rt_set_error("rt_render: block of %d threads needs %zu B of shared memory (max %d)", threads, smemBytes, d.maxSmemOptin);
+        return RT_ERR_INVALID;
+    }
+    KernelFn fn = PickKernelForFeatures(d.dev.features, variant, smem, wantStats, &h->pickedFeatures);
+    h->pickedVariant = variant;
+    h->pickedThreads = threads;
+    RT_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    if (&d == &h->devs[0]) {
+        cudaFuncAttributes fa{};
+        if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(fn)) == cudaSuccess) h->pickedRegisters = fa.numRegs;
+    }
+    const int nTiles = a.tilesX * a.tilesY;
+    const int warpsPerBlock = threads / 32;
+    int blocks = d.smCount * blocksPerSm;
+    blocks = std::max(1, std::min(blocks, (nTiles + warpsPerBlock - 1) / warpsPerBlock));
+    h->fitsSmem = smem;
+    if (end > begin) {
+        fn<<<blocks, threads, smemBytes, stream>>>(d.dev, dc, a);
+        RT_CUDA(cudaGetLastError());
+    }
+    return RT_OK;
+}
+
+int CheckRenderArgs(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p, const char* who)
+{
+    if (!h || !cam || !p) {
+        rt_set_error("%s: NULL argument", who);
+        return RT_ERR_INVALID;
+    }
+    if (cam->image_width <= 0 || cam->image_height <= 0 || cam->max_depth <= 0 || cam->max_depth > 254 ||
+        p->sample_end < p->sample_begin || p->sample_begin < 0) {
+        rt_set_error("%s: bad camera or sample range (max_depth must be 1..254)", who);
+        return RT_ERR_INVALID;
+    }
+    if (cam->samples_per_pixel <= 0) {
+        rt_set_error("%s: samples_per_pixel must be positive (rt_readback divides by it)", who);
+        return RT_ERR_INVALID;
+    }
+    if ((long long)cam->image_width * cam->image_height > 0x7fffffffLL / 3) {
+        rt_set_error("%s: image too large", who);
+        return RT_ERR_INVALID;
+    }
+    if (p->variant < RT_VARIANT_AUTO || p->variant > RT_VARIANT_HITQUEUE) {
+        rt_set_error("%s: unknown variant %d", who, p->variant);
+        return RT_ERR_INVALID;
+    }
+    const long long n = (long long)p->sample_end - p->sample_begin;
+    const long long perDevice = (n + (long long)h->devs.size() - 1) / (long long)h->devs.size();
+    if ((p->variant == RT_VARIANT_HEADTAIL || p->variant == RT_VARIANT_HITQUEUE) && perDevice > RT_HT_MAX_SAMPLES) {
+        rt_set_error("%s: the head/tail and hit-queue variants take at most %d samples per device and call", who, RT_HT_MAX_SAMPLES);
+        return RT_ERR_INVALID;
+    }
+    if (p->variant == RT_VARIANT_WAVEFRONT && p->sample_end >= (1 << 24)) { // its slots pack sample << 8 | bounce
+        rt_set_error("%s: the wavefront variant takes sample indices below 2^24", who);
+        return RT_ERR_INVALID;
+    }
+    if (h->devs.size() > 1 && (p->stream || p->accum)) {
+        rt_set_error("%s: a multi-device handle renders on its own streams into its own accumulators "
+                     "(rt_render_params.stream / .accum must be NULL)", who);
+        return RT_ERR_INVALID;
+    }
+    return RT_OK;
+}
+
+} // namespace
+
+extern "C" {
 
 int rt_scene_pack_info(const rt_scene_desc* scene, const rt_upload_options* opt, rt_pack_info* out)
 {
@@ -265,6 +709,7 @@ int rt_scene_pack_info(const rt_scene_desc* scene, const rt_upload_options* opt,
     return RT_OK;
 }
 
+
 int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt_scene_handle* out)
 {
     if (!scene || !out) {
@@ -285,245 +730,187 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
         rt_set_error("rt_scene_upload: %s", e.what());
         return RT_ERR_INVALID;
     }
+    rt_scene_s* h = new rt_scene_s();
+    h->host = packed; // from here on rt_scene_free(h) releases everything, on every path out
+    h->uploadFlags = o.flags;
     int nDev = 0;
     if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev <= 0) {
-        delete packed;
+        rt_scene_free(h);
         rt_set_error("rt_scene_upload: no CUDA device available (this library has no CPU path)");
         return RT_ERR_NO_DEVICE;
     }
-    if (o.device < 0 || o.device >= nDev) {
-        delete packed;
-        rt_set_error("rt_scene_upload: device %d out of range (have %d)", o.device, nDev);
-        return RT_ERR_INVALID;
+    std::vector<int> ids;
+    if (o.n_devices > 1) {
+        if (o.n_devices > kMaxDevices) {
+            rt_scene_free(h);
+            rt_set_error("rt_scene_upload: at most %d devices", kMaxDevices);
+            return RT_ERR_INVALID;
+        }
+        for (int k = 0; k < o.n_devices; ++k) ids.push_back(o.device_ids ? o.device_ids[k] : k);
+    } else {
+        ids.push_back(o.n_devices == 1 && o.device_ids ? o.device_ids[0] : o.device);
     }
-    RT_CUDA(cudaSetDevice(o.device));
-    rt_scene_s* h = new rt_scene_s();
-    h->device = o.device;
-    h->host = packed;
-    // two attributes, not cudaGetDeviceProperties: the full query costs tens of ms per call
-    RT_CUDA(cudaDeviceGetAttribute(&h->smCount, cudaDevAttrMultiProcessorCount, o.device));
-    RT_CUDA(cudaDeviceGetAttribute(&h->maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
+    for (size_t k = 0; k < ids.size(); ++k) {
+        bool dup = false;
+        for (size_t j = 0; j < k; ++j) dup = dup || ids[j] == ids[k];
+        if (ids[k] < 0 || ids[k] >= nDev || dup) {
+            rt_scene_free(h);
+            rt_set_error("rt_scene_upload: device %d out of range or listed twice (have %d)", ids[k], nDev);
+            return RT_ERR_INVALID;
+        }
+    }
+    DeviceGuard guard;
 
+    // the arena: packed ONCE, the same bytes for every device
     ArenaBuilder ab;
     const size_t oNodes = ab.Add(packed->nodes), oSpheres = ab.Add(packed->spheres);
     const size_t oSphereMat = ab.Add(packed->sphere_material), oMoving = ab.Add(packed->moving);
     const size_t oQuads = ab.Add(packed->quads), oMedia = ab.Add(packed->media), oMaterials = ab.Add(packed->materials);
     const size_t oMatParams = ab.Add(packed->mat_params);
     const size_t oTextures = ab.Add(packed->textures), oPerlins = ab.Add(packed->perlins);
-    std::vector<size_t> oImage(packed->image_bytes.size(), 0);
+    std::vector<DevImage> images(std::max<size_t>(1, packed->image_bytes.size()));
+    std::memset(images.data(), 0, images.size() * sizeof(DevImage));
     for (size_t k = 0; k < packed->image_bytes.size(); ++k)
-        if (!packed->image_bytes[k].empty()) oImage[k] = ab.Add(packed->image_bytes[k]);
-    const size_t oImages = ab.Reserve(std::max<size_t>(1, packed->image_bytes.size()) * sizeof(DevImage));
+        if (!packed->image_bytes[k].empty()) {
+            images[k].offset = (uint32_t)ab.Add(packed->image_bytes[k]);
+            images[k].width = packed->image_w[k];
+            images[k].height = packed->image_h[k];
+        }
+    const size_t oImages = ab.Add(images);
     const size_t oStats = ab.Reserve(4 * sizeof(unsigned long long)), oTile = ab.Reserve(sizeof(unsigned int));
     const size_t oDebug = ab.Reserve(256 * 8 * sizeof(float));
     h->arenaBytes = (ab.bytes.size() + 255) / 256 * 256;
     ab.bytes.resize(h->arenaBytes, 0);
-    {
-        void* p = nullptr;
-        const cudaError_t e = BigMalloc(h->device, &p, h->arenaBytes);
-        if (e != cudaSuccess) {
-            rt_set_error("rt_scene_upload: cudaMalloc of %zu bytes failed: %s", h->arenaBytes, cudaGetErrorString(e));
-            rt_scene_free(h);
-            return RT_ERR_CUDA;
-        }
-        h->arena = static_cast<char*>(p);
+    if (h->arenaBytes >= (1ull << 32)) {
+        rt_scene_free(h);
+        rt_set_error("rt_scene_upload: scene arena of %zu bytes exceeds the 4 GiB the texel offsets address", h->arenaBytes);
+        return RT_ERR_UNSUPPORTED;
     }
-    for (size_t k = 0; k < packed->image_bytes.size(); ++k) { // image table: device addresses inside the arena
-        DevImage im{};
-        im.width = packed->image_w[k];
-        im.height = packed->image_h[k];
-        im.rgb = packed->image_bytes[k].empty() ? nullptr : reinterpret_cast<const uint8_t*>(h->arena + oImage[k]);
-        std::memcpy(ab.bytes.data() + oImages + k * sizeof(DevImage), &im, sizeof im);
-    }
-    {
-        const cudaError_t e = cudaMemcpy(h->arena, ab.bytes.data(), h->arenaBytes, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) {
-            rt_set_error("rt_scene_upload: host-to-device copy failed: %s", cudaGetErrorString(e));
-            rt_scene_free(h);
-            return RT_ERR_CUDA;
-        }
-    }
-    h->deviceBytes = h->arenaBytes;
-    h->dev.nodes = reinterpret_cast<const DevNode*>(h->arena + oNodes);
-    h->dev.spheres = reinterpret_cast<const DevSphere*>(h->arena + oSpheres);
-    h->dev.sphere_material = reinterpret_cast<const int32_t*>(h->arena + oSphereMat);
-    h->dev.moving = reinterpret_cast<const DevMovingSphere*>(h->arena + oMoving);
-    h->dev.quads = reinterpret_cast<const DevQuad*>(h->arena + oQuads);
-    h->dev.media = reinterpret_cast<const DevMedium*>(h->arena + oMedia);
-    h->dev.materials = reinterpret_cast<const DevMaterial*>(h->arena + oMaterials);
-    h->dev.mat_params = reinterpret_cast<const double*>(h->arena + oMatParams);
-    h->dev.textures = reinterpret_cast<const DevTexture*>(h->arena + oTextures);
-    h->dev.perlins = reinterpret_cast<const DevPerlin*>(h->arena + oPerlins);
-    h->dev.images = reinterpret_cast<const DevImage*>(h->arena + oImages);
-    h->stats = reinterpret_cast<unsigned long long*>(h->arena + oStats);
-    h->tileCounter = reinterpret_cast<unsigned int*>(h->arena + oTile);
-    h->debugOut = reinterpret_cast<float*>(h->arena + oDebug);
-    h->dev.root_ref = packed->root_ref;
-    h->dev.n_hoisted = packed->n_hoisted;
-    for (int k = 0; k < RT_MAX_HOISTED; ++k) h->dev.hoisted[k] = packed->hoisted[k];
-    h->dev.n_nodes = (int)packed->nodes.size();
-    h->dev.n_spheres = (int)packed->spheres.size();
-    h->dev.n_moving = (int)packed->moving.size();
-    h->dev.n_quads = (int)packed->quads.size();
-    h->dev.n_media = (int)packed->media.size();
-    h->dev.n_materials = (int)packed->materials.size();
-    h->dev.n_textures = (int)packed->textures.size();
-    h->dev.features = packed->features;
-
     h->stagedBytes = StagedBytes(*packed);
 
+    h->devs.resize(ids.size());
+    for (size_t k = 0; k < ids.size(); ++k) {
+        DeviceCtx& d = h->devs[k];
+        d.device = ids[k];
+        cudaError_t e = cudaSetDevice(d.device);
+        // two attributes, not cudaGetDeviceProperties: the full query costs tens of ms per call
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.smCount, cudaDevAttrMultiProcessorCount, d.device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.device);
+        if (e == cudaSuccess && ids.size() > 1) e = cudaStreamCreateWithFlags(&d.ownStream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&d.evStart);
+        if (e == cudaSuccess) e = cudaEventCreate(&d.evStop);
+        void* p = nullptr;
+        if (e == cudaSuccess) e = BigMalloc(d.device, &p, h->arenaBytes, d.ownStream);
+        d.arena = static_cast<char*>(p);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d.arena, ab.bytes.data(), h->arenaBytes, cudaMemcpyHostToDevice, d.ownStream);
+        if (e != cudaSuccess) {
+            rt_set_error("rt_scene_upload: device %d: %s", d.device, cudaGetErrorString(e));
+            rt_scene_free(h);
+            return RT_ERR_CUDA;
+        }
+        d.lastStream = d.ownStream;
+        d.dev.nodes = reinterpret_cast<const DevNode*>(d.arena + oNodes);
+        d.dev.spheres = reinterpret_cast<const DevSphere*>(d.arena + oSpheres);
+        d.dev.sphere_material = reinterpret_cast<const int32_t*>(d.arena + oSphereMat);
+        d.dev.moving = reinterpret_cast<const DevMovingSphere*>(d.arena + oMoving);
+        d.dev.quads = reinterpret_cast<const DevQuad*>(d.arena + oQuads);
+        d.dev.media = reinterpret_cast<const DevMedium*>(d.arena + oMedia);
+        d.dev.materials = reinterpret_cast<const DevMaterial*>(d.arena + oMaterials);
+        d.dev.mat_params = reinterpret_cast<const double*>(d.arena + oMatParams);
+        d.dev.textures = reinterpret_cast<const DevTexture*>(d.arena + oTextures);
+        d.dev.perlins = reinterpret_cast<const DevPerlin*>(d.arena + oPerlins);
+        d.dev.images = reinterpret_cast<const DevImage*>(d.arena + oImages);
+        d.dev.arena = reinterpret_cast<const uint8_t*>(d.arena);
+        d.stats = reinterpret_cast<unsigned long long*>(d.arena + oStats);
+        d.tileCounter = reinterpret_cast<unsigned int*>(d.arena + oTile);
+        d.debugOut = reinterpret_cast<float*>(d.arena + oDebug);
+        d.dev.root_ref = packed->root_ref;
+        d.dev.n_hoisted = packed->n_hoisted;
+        for (int j = 0; j < RT_MAX_HOISTED; ++j) d.dev.hoisted[j] = packed->hoisted[j];
+        d.dev.n_nodes = (int)packed->nodes.size();
+        d.dev.n_spheres = (int)packed->spheres.size();
+        d.dev.n_moving = (int)packed->moving.size();
+        d.dev.n_quads = (int)packed->quads.size();
+        d.dev.n_media = (int)packed->media.size();
+        d.dev.n_materials = (int)packed->materials.size();
+        d.dev.n_textures = (int)packed->textures.size();
+        d.dev.features = packed->features;
+    }
+    // the pageable host arena dies with this call: the copies must have left it
+    for (DeviceCtx& d : h->devs) {
+        cudaSetDevice(d.device);
+        const cudaError_t e = cudaStreamSynchronize(d.ownStream);
+        if (e != cudaSuccess) {
+            rt_set_error("rt_scene_upload: device %d: %s", d.device, cudaGetErrorString(e));
+            rt_scene_free(h);
+            return RT_ERR_CUDA;
+        }
+    }
+    if (h->devs.size() > 1) {
+        // peer path: device 0 maps the others' memory (NVLink / NVSwitch on a B200 box)
+        h->peerCapable = true;
+        cudaSetDevice(h->devs[0].device);
+        for (size_t k = 1; k < h->devs.size(); ++k) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, h->devs[0].device, h->devs[k].device) != cudaSuccess || !can) {
+                h->peerCapable = false;
+                break;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(h->devs[k].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) h->peerCapable = false;
+            cudaGetLastError(); // (clears "already enabled")
+        }
+    }
+    {
+        cudaSetDevice(h->devs[0].device);
+        cudaError_t e = cudaEventCreate(&h->evReduce0);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->evReduce1);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->evResolve1);
+        if (e != cudaSuccess) {
+            rt_set_error("rt_scene_upload: %s", cudaGetErrorString(e));
+            rt_scene_free(h);
+            return RT_ERR_CUDA;
+        }
+    }
     *out = h;
     return RT_OK;
 }
 
 int rt_render(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p)
 {
-    if (!h || !cam || !p) {
-        rt_set_error("rt_render: NULL argument");
-        return RT_ERR_INVALID;
-    }
-    if (cam->image_width <= 0 || cam->image_height <= 0 || cam->max_depth <= 0 || cam->max_depth > 254 ||
-        p->sample_end < p->sample_begin || p->sample_begin < 0) {
-        rt_set_error("rt_render: bad camera or sample range (max_depth must be 1..254)");
-        return RT_ERR_INVALID;
-    }
-    if ((long long)cam->image_width * cam->image_height > 0x7fffffffLL / 3) {
-        rt_set_error("rt_render: image too large");
-        return RT_ERR_INVALID;
-    }
-    if (p->variant < RT_VARIANT_AUTO || p->variant > RT_VARIANT_HITQUEUE) {
-        rt_set_error("rt_render: unknown variant %d", p->variant);
-        return RT_ERR_INVALID;
-    }
-    // AUTO: the hit-queue kernel unless the sample range exceeds its packed sample index.
-    int variant = p->variant;
-    if (variant == RT_VARIANT_AUTO)
-        variant = (long long)p->sample_end - p->sample_begin <= RT_HT_MAX_SAMPLES ? RT_VARIANT_HITQUEUE : RT_VARIANT_MEGAKERNEL;
-    const bool wave = variant == RT_VARIANT_WAVEFRONT;
-    const bool hitQueue = variant == RT_VARIANT_HITQUEUE;
-    const bool headTail = variant == RT_VARIANT_HEADTAIL || hitQueue; // the two queue kernels share their launch shape
-    if (headTail && (long long)p->sample_end - p->sample_begin > RT_HT_MAX_SAMPLES) {
-        rt_set_error("rt_render: the head/tail and hit-queue variants take at most %d samples per call", RT_HT_MAX_SAMPLES);
-        return RT_ERR_INVALID;
-    }
-    if (wave && p->sample_end >= (1 << 24)) { // its slots pack sample << 8 | bounce
-        rt_set_error("rt_render: the wavefront variant takes sample indices below 2^24");
-        return RT_ERR_INVALID;
-    }
-    RT_CUDA(cudaSetDevice(h->device));
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
+    const int rc0 = CheckRenderArgs(h, cam, p, "rt_render");
+    if (rc0 != RT_OK) return rc0;
+    DeviceGuard guard;
+    const int nDev = (int)h->devs.size();
     const size_t nFloats = (size_t)cam->image_width * cam->image_height * 3;
-    float* accum = p->accum;
-    if (!accum) {
-        if (h->accumFloats != nFloats) {
-            BigFree(h->device, h->accum, h->accumFloats * sizeof(float));
-            h->accum = nullptr;
-            h->accumFloats = 0;
-            RT_CUDA(BigMalloc(h->device, reinterpret_cast<void**>(&h->accum), nFloats * sizeof(float)));
-            h->accumFloats = nFloats;
-            RT_CUDA(cudaMemsetAsync(h->accum, 0, nFloats * sizeof(float), stream));
-        }
-        accum = h->accum;
-    }
-    if (p->clear) {
-        RT_CUDA(cudaMemsetAsync(accum, 0, nFloats * sizeof(float), stream));
-        RT_CUDA(cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), stream));
-    }
-    RT_CUDA(cudaMemsetAsync(h->tileCounter, 0, sizeof(unsigned int), stream));
-
-    const DevCamera dc = rtpack::MakeCamera(*cam);
-    RenderArgs a{};
-    a.accum = accum;
-    a.stats = h->stats;
-    a.tileCounter = h->tileCounter;
-    a.sampleBegin = p->sample_begin;
-    a.sampleEnd = p->sample_end;
-    a.seed = p->seed;
-    a.debugPixel = h->debugPixel;
-    a.debugSample = h->debugSample;
-    a.debugOut = h->debugPixel >= 0 ? h->debugOut : nullptr;
-    // tiles: 8x4 pixels per warp (megakernel: one pixel per lane) or 8x8 (wavefront: 64 path slots)
-    // leaf turn every 2nd step (measured best: 1 -> 11.3, 2 -> 11.5, 4 -> 11.2 Grays/s); development knob in
-    // flags bits 4-5: 1 = every step, 2 = every 4th, 3 = every 8th
-    static const int kLeafMasks[4] = {1, 0, 3, 7};
-    a.megaLeafMask = kLeafMasks[(p->flags >> 4) & 3];
-    // tuning knobs of the wavefront variant (development): flags bits 12-15 slots/32,
-    // 16-20 idle-exit, 21-25 leaf batch, 26-30 refill minimum
-    int waveSlots = ((p->flags >> 12) & 0xf) * 32;
-    a.waveIdleExit = (p->flags >> 16) & 0x1f;
-    a.waveLeafBatch = (p->flags >> 21) & 0x1f;
-    a.waveRefillMin = (p->flags >> 26) & 0x1f;
-    if (a.waveIdleExit <= 0) a.waveIdleExit = 16;
-    if (a.waveLeafBatch <= 0) a.waveLeafBatch = 16;
-    if (a.waveRefillMin <= 0) a.waveRefillMin = 8;
-    auto pad16 = [](size_t b) { return (uint32_t)((b + 15) / 16 * 16); };
-    const rtpack::Packed& pk = *h->host;
-    a.nodesBytes = pad16(std::max<size_t>(1, pk.nodes.size()) * sizeof(DevNode));
-    a.spheresBytes = pad16(std::max<size_t>(1, pk.spheres.size()) * sizeof(DevSphere));
-    a.sphereMatBytes = pad16(std::max<size_t>(1, pk.sphere_material.size()) * sizeof(int32_t));
-    a.movingBytes = pad16(std::max<size_t>(1, pk.moving.size()) * sizeof(DevMovingSphere));
-    a.quadsBytes = pad16(std::max<size_t>(1, pk.quads.size()) * sizeof(DevQuad));
-    a.mediaBytes = pad16(std::max<size_t>(1, pk.media.size()) * sizeof(DevMedium));
-    a.materialsBytes = pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial));
-    a.matParamsBytes = pad16(std::max<size_t>(1, pk.mat_params.size()) * sizeof(double));
-
-    const int featClassEarly = h->dev.features == 0 ? 0 : ((h->dev.features & ~(RT_FEAT_MOVING | RT_FEAT_TEXTURE)) == 0 ? (RT_FEAT_MOVING | RT_FEAT_TEXTURE) : 31);
-    const int maxThreads = wave ? 512 : (headTail ? HtMaxThreads(featClassEarly) : MegaMaxThreads(h->dev.features == 0 ? 0 : 1));
-    int threads = p->block_threads > 0 ? p->block_threads : maxThreads;
-    threads = std::max(32, std::min(maxThreads, (threads / 32) * 32));
-    int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;
-    const int stackLevels = std::max(3, std::min(kMaxStackLevels, h->host->max_depth + 3)); // + sentinel slot
-    a.stackLevels = stackLevels;
-    if (wave) {
-        threads = std::min(threads, 512); // __launch_bounds__(512, 1)
-        blocksPerSm = 1;
-    }
-    const int featClass = h->dev.features == 0 ? kFeatSpheres : ((h->dev.features & ~kFeatMotion) == 0 ? kFeatMotion : kFeatAll);
-    const size_t warpBytes = hitQueue ? HqWarpBytes(featClass) : HtWarpBytes(featClass);
-    if (headTail && p->block_threads <= 0 && !(p->flags & 0x200)) {
-        // the largest block whose stacks + queues still leave room for the scene in shared memory
-        // (if none does, the scene stays in global memory and the block is as large as registers allow)
-        threads = maxThreads;
-        for (int cand = maxThreads; cand >= 384; cand -= 128)
-            if ((size_t)cand * 4 * stackLevels + (size_t)(cand / 32) * warpBytes + 16 + h->stagedBytes <=
-                (size_t)h->maxSmemOptin) {
-                threads = cand;
-                break;
+    const long long n = (long long)p->sample_end - p->sample_begin;
+    for (int k = 0; k < nDev; ++k) {
+        DeviceCtx& d = h->devs[k];
+        RT_CUDA(cudaSetDevice(d.device));
+        cudaStream_t stream = nDev > 1 ? d.ownStream : reinterpret_cast<cudaStream_t>(p->stream);
+        float* accum = p->accum;
+        bool fresh = false;
+        if (!accum) {
+            if (d.accumFloats != nFloats) {
+                BigFree(d.device, d.accum, d.accumFloats * sizeof(float), d.lastStream);
+                d.accum = nullptr;
+                d.accumFloats = 0;
+                RT_CUDA(BigMalloc(d.device, reinterpret_cast<void**>(&d.accum), nFloats * sizeof(float), stream));
+                d.accumFloats = nFloats;
+                fresh = true;
             }
+            accum = d.accum;
+        }
+        // device k of G renders the k-th slice of the sample range (bench.py / multigpu.py use the same split)
+        const int begin = p->sample_begin + (int)((n * k) / nDev), end = p->sample_begin + (int)((n * (k + 1)) / nDev);
+        d.sampleBegin = begin;
+        d.sampleEnd = end;
+        RT_CUDA(cudaEventRecord(d.evStart, stream));
+        const int rc = LaunchOn(h, d, cam, p, begin, end, accum, stream, p->clear != 0 || fresh);
+        if (rc != RT_OK) return rc;
+        RT_CUDA(cudaEventRecord(d.evStop, stream));
+        d.lastStream = stream;
     }
-    const size_t stackBytes = (size_t)threads * 4 * stackLevels;
-    size_t poolBytes = headTail ? (size_t)(threads / 32) * warpBytes + 16 : 0;
-    if (wave) {
-        // 64 slots (an 8x8 tile) measured best: 96 or 128 fill SHADE/GEN chunks better but cost more shared
-        // memory traffic and longer tile tails (profiles/r1_wavefront_parameter_sweep.json)
-        auto bytesFor = [&](int slots) { return (size_t)(threads / 32) * PoolBytes(slots) + 16; };
-        if (waveSlots < 64 || waveSlots > 128) waveSlots = 64;
-        poolBytes = bytesFor(waveSlots);
-    }
-    a.waveSlots = waveSlots;
-    const int tileH = wave ? waveSlots / 8 : kTileH;
-    a.tilesX = (cam->image_width + kTileW - 1) / kTileW;
-    a.tilesY = (cam->image_height + tileH - 1) / tileH;
-    const bool wantStats = (p->flags & 0x100) != 0 || a.debugOut != nullptr;
-    const bool smem = !(p->flags & 0x200) &&
-                      stackBytes + poolBytes + h->stagedBytes <= (size_t)h->maxSmemOptin / (size_t)blocksPerSm;
-    const size_t smemBytes = stackBytes + poolBytes + (smem ? h->stagedBytes : 0);
-    if (smemBytes > (size_t)h->maxSmemOptin) {
-        rt_set_error("rt_render: block of %d threads needs %zu B of shared memory (max %d)", threads, smemBytes,
-                     h->maxSmemOptin);
-        return RT_ERR_INVALID;
-    }
-    KernelFn fn = PickKernelForFeatures(h->dev.features, variant, smem, wantStats, &h->pickedFeatures);
-    h->pickedVariant = variant;
-    RT_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    const int nTiles = a.tilesX * a.tilesY;
-    const int warpsPerBlock = threads / 32;
-    int blocks = h->smCount * blocksPerSm;
-    blocks = std::max(1, std::min(blocks, (nTiles + warpsPerBlock - 1) / warpsPerBlock));
-    h->fitsSmem = smem;
-    fn<<<blocks, threads, smemBytes, stream>>>(h->dev, dc, a);
-    RT_CUDA(cudaGetLastError());
-    h->lastStream = stream;
     h->lastCam = *cam;
     h->rendered = true;
     return RT_OK;
@@ -535,9 +922,9 @@ int rt_accum_ptr(rt_scene_handle h, float** dev_ptr, uint64_t* n_floats)
         rt_set_error("rt_accum_ptr: NULL argument");
         return RT_ERR_INVALID;
     }
-    *dev_ptr = h->accum;
-    if (n_floats) *n_floats = h->accumFloats;
-    return h->accum ? RT_OK : RT_ERR_STATE;
+    *dev_ptr = h->devs[0].accum;
+    if (n_floats) *n_floats = h->devs[0].accumFloats;
+    return h->devs[0].accum ? RT_OK : RT_ERR_STATE;
 }
 
 int rt_sync(rt_scene_handle h)
@@ -546,8 +933,11 @@ int rt_sync(rt_scene_handle h)
         rt_set_error("rt_sync: NULL handle");
         return RT_ERR_INVALID;
     }
-    RT_CUDA(cudaSetDevice(h->device));
-    RT_CUDA(cudaStreamSynchronize(h->lastStream));
+    DeviceGuard guard;
+    for (DeviceCtx& d : h->devs) {
+        RT_CUDA(cudaSetDevice(d.device));
+        RT_CUDA(cudaStreamSynchronize(d.lastStream));
+    }
     return RT_OK;
 }
 
@@ -561,61 +951,209 @@ int rt_readback(rt_scene_handle h, const float* accum, float* linear_rgb, uint8_
         rt_set_error("rt_readback: nothing rendered yet");
         return RT_ERR_STATE;
     }
-    RT_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard;
+    DeviceCtx& d0 = h->devs[0];
+    const int nDev = (int)h->devs.size();
     const int W = h->lastCam.image_width, H = h->lastCam.image_height;
     const size_t nFloats = (size_t)W * H * 3;
-    const float* src = accum ? accum : h->accum;
-    if (!src && (linear_rgb || srgb8)) {
+    if (accum && nDev > 1) {
+        rt_set_error("rt_readback: a multi-device handle reduces its own accumulators (`accum` must be NULL)");
+        return RT_ERR_INVALID;
+    }
+    if (!accum && !d0.accum && (linear_rgb || srgb8)) {
         rt_set_error("rt_readback: no accumulator (the render used a caller-owned one: pass it as `accum`)");
         return RT_ERR_STATE;
     }
-    cudaStream_t stream = h->lastStream;
-    if (linear_rgb || srgb8) {
-        if (linear_rgb && h->linearStageFloats < nFloats) {
-            BigFree(h->device, h->linearStage, h->linearStageFloats * sizeof(float));
-            h->linearStage = nullptr;
-            h->linearStageFloats = 0;
-            RT_CUDA(BigMalloc(h->device, reinterpret_cast<void**>(&h->linearStage), nFloats * sizeof(float)));
-            h->linearStageFloats = nFloats;
-        }
-        if (srgb8 && h->srgbStageBytes < nFloats) {
-            BigFree(h->device, h->srgbStage, h->srgbStageBytes);
-            h->srgbStage = nullptr;
-            h->srgbStageBytes = 0;
-            RT_CUDA(BigMalloc(h->device, reinterpret_cast<void**>(&h->srgbStage), nFloats));
-            h->srgbStageBytes = nFloats;
-        }
-        const int n = W * H;
+    RT_CUDA(cudaSetDevice(d0.device));
+    cudaStream_t s0 = d0.lastStream;
+    h->timedReadback = true;
+    const bool needFrame = linear_rgb || srgb8;
+    if (needFrame || (nDev > 1 && d0.accum)) {
         const float invSpp = 1.0f / (float)h->lastCam.samples_per_pixel;
-        ResolveKernel<<<(n + 255) / 256, 256, 0, stream>>>(src, linear_rgb ? h->linearStage : nullptr,
-                                                           srgb8 ? h->srgbStage : nullptr, W, H, invSpp);
-        RT_CUDA(cudaGetLastError());
+        const int rc = QueueReduceResolve(h, accum, 0, linear_rgb != nullptr, srgb8 != nullptr, invSpp);
+        if (rc != RT_OK) return rc;
         if (linear_rgb)
-            RT_CUDA(cudaMemcpyAsync(linear_rgb, h->linearStage, nFloats * sizeof(float), cudaMemcpyDeviceToHost, stream));
-        if (srgb8) RT_CUDA(cudaMemcpyAsync(srgb8, h->srgbStage, nFloats, cudaMemcpyDeviceToHost, stream));
+            RT_CUDA(cudaMemcpyAsync(linear_rgb, h->linearStage[0], nFloats * sizeof(float), cudaMemcpyDeviceToHost, s0));
+        if (srgb8) RT_CUDA(cudaMemcpyAsync(srgb8, h->srgbStage[0], nFloats, cudaMemcpyDeviceToHost, s0));
+        RT_CUDA(cudaEventRecord(h->evResolve1, s0));
+    } else {
+        h->timedReadback = false;
     }
     if (stats) {
-        unsigned long long s[4];
-        RT_CUDA(cudaMemcpyAsync(s, h->stats, sizeof s, cudaMemcpyDeviceToHost, stream));
-        RT_CUDA(cudaStreamSynchronize(stream));
-        stats->rays = s[0];
-        stats->paths = s[1];
-        stats->node_tests = s[2];
-        stats->prim_tests = s[3];
+        std::memset(stats, 0, sizeof *stats);
+        for (DeviceCtx& d : h->devs) {
+            unsigned long long s[4];
+            RT_CUDA(cudaSetDevice(d.device));
+            RT_CUDA(cudaMemcpyAsync(s, d.stats, sizeof s, cudaMemcpyDeviceToHost, d.lastStream));
+            RT_CUDA(cudaStreamSynchronize(d.lastStream));
+            stats->rays += s[0];
+            stats->paths += s[1];
+            stats->node_tests += s[2];
+            stats->prim_tests += s[3];
+        }
     }
-    RT_CUDA(cudaStreamSynchronize(stream));
+    for (DeviceCtx& d : h->devs) {
+        RT_CUDA(cudaSetDevice(d.device));
+        RT_CUDA(cudaStreamSynchronize(d.lastStream));
+    }
+    return RT_OK;
+}
+
+int rt_render_progressive(rt_scene_handle h, const rt_camera* cam, const rt_render_params* p, int32_t batch,
+                          int32_t want_linear, int32_t want_srgb8, rt_progress_fn fn, void* user)
+{
+    const int rc0 = CheckRenderArgs(h, cam, p, "rt_render_progressive");
+    if (rc0 != RT_OK) return rc0;
+    if (batch <= 0 || !fn || (!want_linear && !want_srgb8) || p->accum) {
+        rt_set_error("rt_render_progressive: needs batch > 0, a callback, an output format, and the handle's own accumulator");
+        return RT_ERR_INVALID;
+    }
+    if (!p->clear) {
+        rt_set_error("rt_render_progressive: the mean is taken over the samples of this call: rt_render_params.clear must be 1");
+        return RT_ERR_INVALID;
+    }
+    DeviceGuard guard;
+    DeviceCtx& d0 = h->devs[0];
+    const size_t nFloats = (size_t)cam->image_width * cam->image_height * 3;
+    RT_CUDA(cudaSetDevice(d0.device));
+    if (!h->copyStream) RT_CUDA(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+    if (want_linear && h->hostLinearFloats < nFloats) {
+        for (int k = 0; k < 2; ++k) {
+            if (h->hostLinear[k]) cudaFreeHost(h->hostLinear[k]);
+            h->hostLinear[k] = nullptr;
+        }
+        h->hostLinearFloats = 0;
+        for (int k = 0; k < 2; ++k) RT_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->hostLinear[k]), nFloats * sizeof(float), cudaHostAllocDefault));
+        h->hostLinearFloats = nFloats;
+    }
+    if (want_srgb8 && h->hostSrgbBytes < nFloats) {
+        for (int k = 0; k < 2; ++k) {
+            if (h->hostSrgb[k]) cudaFreeHost(h->hostSrgb[k]);
+            h->hostSrgb[k] = nullptr;
+        }
+        h->hostSrgbBytes = 0;
+        for (int k = 0; k < 2; ++k) RT_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->hostSrgb[k]), nFloats, cudaHostAllocDefault));
+        h->hostSrgbBytes = nFloats;
+    }
+    cudaEvent_t resolved[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; ++k) {
+        RT_CUDA(cudaEventCreateWithFlags(&resolved[k], cudaEventDisableTiming));
+        RT_CUDA(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+    }
+    const int total = p->sample_end - p->sample_begin;
+    int rc = RT_OK, done = 0, pendingDone = 0, b = 0;
+    bool pending = false;
+    auto deliver = [&](int set, int samples) -> int {
+        RT_CUDA(cudaEventSynchronize(copied[set]));
+        fn(user, want_linear ? h->hostLinear[set] : nullptr, want_srgb8 ? h->hostSrgb[set] : nullptr, samples, total);
+        return RT_OK;
+    };
+    h->timedReadback = false;
+    while (done < total && rc == RT_OK) {
+        const int set = b & 1;
+        rt_render_params q = *p;
+        q.sample_begin = p->sample_begin + done;
+        q.sample_end = std::min(p->sample_end, q.sample_begin + batch);
+        q.clear = b == 0 ? 1 : 0;
+        rc = rt_render(h, cam, &q);
+        if (rc != RT_OK) break;
+        done = q.sample_end - p->sample_begin;
+        RT_CUDA(cudaSetDevice(d0.device));
+        cudaStream_t s0 = d0.lastStream;
+        // the resolve runs on the render stream, between two batches (it reads the accumulator the next batch
+        // adds to); only the device-to-host copy overlaps the next batch.  Stage set `set` was last read by the copy
+        // of batch b-2.
+        if (b >= 2) RT_CUDA(cudaStreamWaitEvent(s0, copied[set], 0));
+        rc = QueueReduceResolve(h, nullptr, set, want_linear != 0, want_srgb8 != 0, 1.0f / (float)done);
+        if (rc != RT_OK) break;
+        RT_CUDA(cudaEventRecord(resolved[set], s0));
+        RT_CUDA(cudaStreamWaitEvent(h->copyStream, resolved[set], 0));
+        if (want_linear)
+            RT_CUDA(cudaMemcpyAsync(h->hostLinear[set], h->linearStage[set], nFloats * sizeof(float), cudaMemcpyDeviceToHost, h->copyStream));
+        if (want_srgb8) RT_CUDA(cudaMemcpyAsync(h->hostSrgb[set], h->srgbStage[set], nFloats, cudaMemcpyDeviceToHost, h->copyStream));
+        RT_CUDA(cudaEventRecord(copied[set], h->copyStream));
+        // hand over the PREVIOUS batch while this one renders
+        if (pending) rc = deliver(set ^ 1, pendingDone);
+        pending = true;
+        pendingDone = done;
+        ++b;
+    }
+    if (rc == RT_OK && pending) rc = deliver((b - 1) & 1, pendingDone);
+    cudaSetDevice(d0.device);
+    cudaStreamSynchronize(h->copyStream);
+    for (int k = 0; k < 2; ++k) {
+        if (resolved[k]) cudaEventDestroy(resolved[k]);
+        if (copied[k]) cudaEventDestroy(copied[k]);
+    }
+    if (rc == RT_OK) rc = rt_sync(h);
+    rt_camera c = *cam;
+    c.samples_per_pixel = std::max(1, total); // a later rt_readback of this handle reports the same mean
+    h->lastCam = c;
+    return rc;
+}
+
+int rt_get_timing(rt_scene_handle h, rt_timing* out)
+{
+    if (!h || !out) {
+        rt_set_error("rt_get_timing: NULL argument");
+        return RT_ERR_INVALID;
+    }
+    if (!h->rendered) {
+        rt_set_error("rt_get_timing: nothing rendered yet");
+        return RT_ERR_STATE;
+    }
+    DeviceGuard guard;
+    std::memset(out, 0, sizeof *out);
+    out->n_devices = (int32_t)h->devs.size();
+    for (size_t k = 0; k < h->devs.size() && k < 16; ++k) {
+        DeviceCtx& d = h->devs[k];
+        RT_CUDA(cudaSetDevice(d.device));
+        RT_CUDA(cudaStreamSynchronize(d.lastStream));
+    }
+    RT_CUDA(cudaSetDevice(h->devs[0].device));
+    if (h->timedReadback) {
+        RT_CUDA(cudaEventElapsedTime(&out->reduce_ms, h->evReduce0, h->evReduce1));
+        RT_CUDA(cudaEventElapsedTime(&out->resolve_ms, h->evReduce1, h->evResolve1));
+    }
+    // (device 0's evStop doubles as the "reduced" marker of a multi-device readback: its render time is only
+    // meaningful before rt_readback, which is when bench.py asks)
+    for (size_t k = 0; k < h->devs.size() && k < 16; ++k) {
+        DeviceCtx& d = h->devs[k];
+        RT_CUDA(cudaSetDevice(d.device));
+        if (cudaEventElapsedTime(&out->render_ms[k], d.evStart, d.evStop) != cudaSuccess) {
+            cudaGetLastError();
+            out->render_ms[k] = 0.0f;
+        }
+    }
     return RT_OK;
 }
 
 int rt_scene_free(rt_scene_handle h)
 {
     if (!h) return RT_OK;
-    cudaSetDevice(h->device);
-    if (h->rendered) cudaStreamSynchronize(h->lastStream); // recycled buffers must be idle
-    BigFree(h->device, h->arena, h->arenaBytes);
-    BigFree(h->device, h->accum, h->accumFloats * sizeof(float));
-    BigFree(h->device, h->linearStage, h->linearStageFloats * sizeof(float));
-    BigFree(h->device, h->srgbStage, h->srgbStageBytes);
+    DeviceGuard guard;
+    if (!h->devs.empty()) {
+        DeviceCtx& d0 = h->devs[0];
+        if (cudaSetDevice(d0.device) == cudaSuccess) {
+            if (h->copyStream) {
+                cudaStreamSynchronize(h->copyStream);
+                cudaStreamDestroy(h->copyStream);
+            }
+            cudaStream_t s0 = d0.lastStream ? d0.lastStream : d0.ownStream;
+            for (int k = 0; k < 2; ++k) {
+                BigFree(d0.device, h->linearStage[k], h->linearStageFloats[k] * sizeof(float), s0);
+                BigFree(d0.device, h->srgbStage[k], h->srgbStageBytes[k], s0);
+                if (h->hostLinear[k]) cudaFreeHost(h->hostLinear[k]);
+                if (h->hostSrgb[k]) cudaFreeHost(h->hostSrgb[k]);
+            }
+            if (h->evReduce0) cudaEventDestroy(h->evReduce0);
+            if (h->evReduce1) cudaEventDestroy(h->evReduce1);
+            if (h->evResolve1) cudaEventDestroy(h->evResolve1);
+        }
+    }
+    for (NcclComm c : h->comms)
+        if (c && gNccl.ok) gNccl.CommDestroy(c);
+    for (DeviceCtx& d : h->devs) FreeDevice(h, d);
     delete h->host;
     delete h;
     return RT_OK;
@@ -628,8 +1166,16 @@ int rt_release_cached_memory(void)
         std::lock_guard<std::mutex> lock(gBigMutex);
         blocks.swap(gBigCache);
     }
+    if (blocks.empty()) return RT_OK;
+    DeviceGuard guard;
     for (const BigBlock& b : blocks) {
-        if (cudaSetDevice(b.device) == cudaSuccess) cudaFree(b.ptr);
+        if (cudaSetDevice(b.device) == cudaSuccess) {
+            if (b.idle) {
+                cudaEventSynchronize(b.idle);
+                cudaEventDestroy(b.idle);
+            }
+            cudaFree(b.ptr);
+        }
     }
     return RT_OK;
 }
@@ -640,15 +1186,20 @@ int rt_scene_get_info(rt_scene_handle h, rt_scene_info* info)
         rt_set_error("rt_scene_get_info: NULL argument");
         return RT_ERR_INVALID;
     }
+    const DevScene& dev = h->devs[0].dev;
     std::memset(info, 0, sizeof *info);
-    info->n_prims_baked = h->dev.n_spheres + h->dev.n_moving + h->dev.n_quads;
-    info->n_nodes = h->dev.n_nodes;
-    info->n_media = h->dev.n_media;
+    info->n_prims_baked = dev.n_spheres + dev.n_moving + dev.n_quads;
+    info->n_nodes = dev.n_nodes;
+    info->n_media = dev.n_media;
     info->max_depth_bvh = h->host->max_depth;
-    info->features = h->dev.features;
+    info->features = dev.features;
     info->scene_in_smem = h->fitsSmem ? 1 : 0;
     info->variant = h->pickedVariant;
-    info->device_bytes = h->deviceBytes;
+    info->n_devices = (int32_t)h->devs.size();
+    info->reduce_path = h->reducePath;
+    info->block_threads = h->pickedThreads;
+    info->registers = h->pickedRegisters;
+    info->device_bytes = h->arenaBytes;
     for (int k = 0; k < 8; ++k) info->medium_visits[k] = h->host->medium_visits[k];
     return RT_OK;
 }
@@ -660,8 +1211,14 @@ int rt_debug_trace_path(rt_scene_handle h, const rt_camera* cam, const rt_render
         rt_set_error("rt_debug_trace_path: bad argument");
         return RT_ERR_INVALID;
     }
-    RT_CUDA(cudaSetDevice(h->device));
-    RT_CUDA(cudaMemset(h->debugOut, 0, 256 * 8 * sizeof(float)));
+    if (h->devs.size() != 1) {
+        rt_set_error("rt_debug_trace_path: single-device handles only");
+        return RT_ERR_INVALID;
+    }
+    DeviceGuard guard;
+    DeviceCtx& d = h->devs[0];
+    RT_CUDA(cudaSetDevice(d.device));
+    RT_CUDA(cudaMemset(d.debugOut, 0, 256 * 8 * sizeof(float)));
     h->debugPixel = pixel;
     h->debugSample = sample;
     rt_render_params q = *p;
@@ -670,8 +1227,9 @@ int rt_debug_trace_path(rt_scene_handle h, const rt_camera* cam, const rt_render
     const int rc = rt_render(h, cam, &q);
     h->debugPixel = h->debugSample = -1;
     if (rc != RT_OK) return rc;
-    RT_CUDA(cudaStreamSynchronize(h->lastStream));
-    RT_CUDA(cudaMemcpy(records, h->debugOut, (size_t)max_records * 8 * sizeof(float), cudaMemcpyDeviceToHost));
+    RT_CUDA(cudaSetDevice(d.device));
+    RT_CUDA(cudaStreamSynchronize(d.lastStream));
+    RT_CUDA(cudaMemcpy(records, d.debugOut, (size_t)max_records * 8 * sizeof(float), cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 
@@ -679,60 +1237,6 @@ float rt_rng_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t sl
 {
     const rt_u4 b = rt_rng_block(seed, pixel, sample, slot, domain, dim >> 2);
     return rt_bits_to_u01(rt_u4_lane(b, dim & 3u));
-}
-
-// P3 text: the reference's format (kernel.cu:696-723), byte for byte; digits come from a
-// 256-entry table instead of a printf per pixel (4K: 95 MB of text in ~0.1 s instead of ~2 s).
-static int WritePpm(const char* path, const uint8_t* srgb8, int32_t width, int32_t height, bool binary, const char* who)
-{
-    if (!path || !srgb8 || width <= 0 || height <= 0) {
-        rt_set_error("%s: bad argument", who);
-        return RT_ERR_INVALID;
-    }
-    FILE* f = std::fopen(path, "wb");
-    if (!f) {
-        rt_set_error("%s: cannot open %s", who, path);
-        return RT_ERR_INVALID;
-    }
-    const size_t n = (size_t)width * height;
-    bool ok = std::fprintf(f, "%s\n%d %d\n255\n", binary ? "P6" : "P3", width, height) > 0;
-    if (binary) {
-        ok = ok && std::fwrite(srgb8, 1, n * 3, f) == n * 3;
-    } else {
-        char digits[256][4];
-        uint8_t len[256];
-        for (int v = 0; v < 256; ++v) len[v] = (uint8_t)std::snprintf(digits[v], sizeof digits[v], "%d", v);
-        std::vector<char> buf;
-        buf.reserve((1u << 20) + 16);
-        for (size_t k = 0; k < n && ok; ++k) {
-            for (int c = 0; c < 3; ++c) {
-                const uint8_t v = srgb8[3 * k + c];
-                buf.insert(buf.end(), digits[v], digits[v] + len[v]);
-                buf.push_back(c == 2 ? '\n' : ' ');
-            }
-            if (buf.size() >= (1u << 20)) {
-                ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-                buf.clear();
-            }
-        }
-        ok = ok && std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-    }
-    ok = (std::fclose(f) == 0) && ok;
-    if (!ok) {
-        rt_set_error("%s: write to %s failed", who, path);
-        return RT_ERR_INVALID;
-    }
-    return RT_OK;
-}
-
-int rt_write_ppm(const char* path, const uint8_t* srgb8, int32_t width, int32_t height)
-{
-    return WritePpm(path, srgb8, width, height, false, "rt_write_ppm");
-}
-
-int rt_write_ppm_binary(const char* path, const uint8_t* srgb8, int32_t width, int32_t height)
-{
-    return WritePpm(path, srgb8, width, height, true, "rt_write_ppm_binary");
 }
 
 int rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_count)
@@ -791,6 +1295,7 @@ int rt_abi_sizeof(const char* name)
     if (n == "rt_stats") return (int)sizeof(rt_stats);
     if (n == "rt_scene_info") return (int)sizeof(rt_scene_info);
     if (n == "rt_pack_info") return (int)sizeof(rt_pack_info);
+    if (n == "rt_timing") return (int)sizeof(rt_timing);
     return -1;
 }
 

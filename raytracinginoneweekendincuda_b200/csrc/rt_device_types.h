@@ -134,9 +134,12 @@ struct RT_ALIGN(16) DevPerlin {
     uint8_t _p[256];
 };
 
-struct DevImage {
-    const uint8_t* rgb;
-    int32_t width, height;
+// Texels live in the scene arena; the record holds their OFFSET from the arena base, so that the arena is one
+// position-independent block that any device can receive as it is.
+struct RT_ALIGN(16) DevImage {
+    uint32_t offset; // bytes from DevScene.arena to the first texel (RGB8, row 0 = top)
+    int32_t width, height; // 0 x 0: no image (-> cyan, Texture.h:113-114)
+    uint32_t _p;
 };
 
 // Scene feature bits: select the kernel instantiation.
@@ -158,6 +161,7 @@ struct DevScene {
     const DevTexture* textures;
     const DevPerlin* perlins;
     const DevImage* images;
+    const uint8_t* arena; // base of the scene arena (image texel offsets are relative to it)
     uint32_t root_ref;
     uint32_t hoisted[RT_MAX_HOISTED];
     int32_t n_hoisted;

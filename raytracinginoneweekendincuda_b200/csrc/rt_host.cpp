@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/rt/scenes.hpp"
 #include "../../include/rt_scenes_c.h"
@@ -85,6 +86,60 @@ void rt_image_linearize_rgb8(const uint8_t* srgb, uint8_t* out, uint64_t n)
         lut[x] = f <= 0.0f ? 0 : (1.0f <= f ? 255 : (uint8_t)(256.0f * f));
     }
     for (uint64_t k = 0; k < n; ++k) out[k] = lut[srgb[k]];
+}
+
+// P3 text: the reference's format (kernel.cu:696-723), byte for byte; digits come from a
+// 256-entry table instead of a printf per pixel (4K: 95 MB of text in ~0.1 s instead of ~2 s).
+static int WritePpm(const char* path, const uint8_t* srgb8, int32_t width, int32_t height, bool binary, const char* who)
+{
+    if (!path || !srgb8 || width <= 0 || height <= 0) {
+        rt_set_error("%s: bad argument", who);
+        return RT_ERR_INVALID;
+    }
+    FILE* f = std::fopen(path, "wb");
+    if (!f) {
+        rt_set_error("%s: cannot open %s", who, path);
+        return RT_ERR_INVALID;
+    }
+    const size_t n = (size_t)width * height;
+    bool ok = std::fprintf(f, "%s\n%d %d\n255\n", binary ? "P6" : "P3", width, height) > 0;
+    if (binary) {
+        ok = ok && std::fwrite(srgb8, 1, n * 3, f) == n * 3;
+    } else {
+        char digits[256][4];
+        uint8_t len[256];
+        for (int v = 0; v < 256; ++v) len[v] = (uint8_t)std::snprintf(digits[v], sizeof digits[v], "%d", v);
+        std::vector<char> buf;
+        buf.reserve((1u << 20) + 16);
+        for (size_t k = 0; k < n && ok; ++k) {
+            for (int c = 0; c < 3; ++c) {
+                const uint8_t v = srgb8[3 * k + c];
+                buf.insert(buf.end(), digits[v], digits[v] + len[v]);
+                buf.push_back(c == 2 ? '\n' : ' ');
+            }
+            if (buf.size() >= (1u << 20)) {
+                ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+                buf.clear();
+            }
+        }
+        ok = ok && std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) {
+        rt_set_error("%s: write to %s failed", who, path);
+        return RT_ERR_INVALID;
+    }
+    return RT_OK;
+}
+
+int rt_write_ppm(const char* path, const uint8_t* srgb8, int32_t width, int32_t height)
+{
+    return WritePpm(path, srgb8, width, height, false, "rt_write_ppm");
+}
+
+int rt_write_ppm_binary(const char* path, const uint8_t* srgb8, int32_t width, int32_t height)
+{
+    return WritePpm(path, srgb8, width, height, true, "rt_write_ppm_binary");
 }
 
 } // extern "C"

@@ -92,6 +92,7 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
     sv.textures = scene.textures;
     sv.perlins = scene.perlins;
     sv.images = scene.images;
+    sv.arena = scene.arena;
     sv.root_ref = scene.root_ref;
     if constexpr (SMEM)
         if (!(sv.root_ref & RT_REF_LEAF)) sv.root_ref = sv.nodes.a + sv.root_ref * 32u;

@@ -153,6 +153,7 @@ template <bool SMEM> struct SceneView {
     const DevTexture* textures;
     const DevPerlin* perlins;
     const DevImage* images;
+    const uint8_t* arena;
     uint32_t root_ref;
     uint32_t hoisted[RT_MAX_HOISTED]; // leaf refs every ray tests before it enters the tree
     int n_hoisted;
@@ -182,10 +183,11 @@ struct Ray {
 };
 
 // What traversal needs besides the ray: fp32 copies for the slab test.
-// RT_SLAB_FFMA (build option, A/B): also keep |1/d|, so that entry/exit = fma(-+e, |1/d|, t_centre) -- 9 FFMA per box
-// instead of 3 FFMA + 3 FMUL + 6 FADD -- at the price of three more live registers in the traversal loop.
+// RT_SLAB_FFMA (build option; default on): also keep |1/d|, so that entry/exit = fma(-+e, |1/d|, t_centre) -- 9 FFMA
+// per box instead of 3 FFMA + 3 FMUL + 6 FADD -- at the price of three more live registers in the traversal loop.
+// Measured on the hit-queue kernel (4K Book 1, 64 spp): 19.49 -> 20.30 Grays/s (profiles/README.md, round 2).
 #ifndef RT_SLAB_FFMA
-#define RT_SLAB_FFMA 0
+#define RT_SLAB_FFMA 1
 #endif
 struct RaySlab {
     f3 inv;     // 1/d
@@ -737,7 +739,7 @@ template <int FEAT, bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv,
             const int idx = __ldg(&t->index);
             if (idx < 0) return make_f3(0.0f, 1.0f, 1.0f);
             const DevImage im = sv.images[idx];
-            if (im.height <= 0 || im.rgb == nullptr) return make_f3(0.0f, 1.0f, 1.0f);
+            if (im.height <= 0 || im.width <= 0) return make_f3(0.0f, 1.0f, 1.0f);
             float u = h.u, v = h.v;
             if (sphereLike) SphereUV(h.outward, u, v);
             u = fminf(fmaxf(u, 0.0f), 1.0f);
@@ -745,7 +747,7 @@ template <int FEAT, bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv,
             int i = (int)(u * (float)im.width), j = (int)(v * (float)im.height);
             if (i >= im.width) i = im.width - 1;
             if (j >= im.height) j = im.height - 1;
-            const uint8_t* px = im.rgb + ((size_t)j * im.width + i) * 3;
+            const uint8_t* px = sv.arena + im.offset + ((size_t)j * im.width + i) * 3;
             const float cs = 1.0f / 255.0f;
             return make_f3(cs * __ldg(px), cs * __ldg(px + 1), cs * __ldg(px + 2));
         }

@@ -34,8 +34,7 @@ def built():
     cli = os.path.join(ROOT, "raytracinginoneweekendincuda_b200", "rt_cli")
     if not (os.path.exists(_build.lib_path()) and os.path.exists(cli)):
         _build.build_product()
-    if not os.path.exists(O.oracle_path()):
-        O.build_oracle()
+    O.build_oracle()  # (a no-op unless rt_oracle.cpp or the ABI headers are newer than liboracle.so)
     return True
 
 
@@ -61,10 +60,10 @@ def ref_stream():
 
 @pytest.fixture(scope="session")
 def earth():
-    from raytracinginoneweekendincuda_b200 import load_earth_fixture
-    e = load_earth_fixture()
-    assert e is not None, "tests/golden/earthmap_rgb8.npz missing"
-    return e
+    """The earthmap texels as the reference's RtwImage produces them (fixture made by golden/make_golden.py)."""
+    path = os.path.join(GOLDEN, "earthmap_rgb8.npz")
+    assert os.path.exists(path), "tests/golden/earthmap_rgb8.npz missing"
+    return np.ascontiguousarray(np.load(path)["rgb"])
 
 
 def oracle_render(oracle, scene, cam, s0, s1, seed=1984, bvh=1, precision=64, threads=0):

@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported(lib, header):
 def test_struct_sizes_match_the_library(lib):
     for name in ["rt_prim", "rt_xform", "rt_object", "rt_material", "rt_texture", "rt_perlin", "rt_image",
                  "rt_scene_desc", "rt_camera", "rt_upload_options", "rt_render_params", "rt_stats", "rt_scene_info",
-                 "rt_pack_info"]:
+                 "rt_pack_info", "rt_timing"]:
         assert lib.rt_abi_sizeof(name.encode()) == C.sizeof(getattr(A, name)), name
 
 

@@ -12,9 +12,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch  # noqa: E402
 
-from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, library_path, load_earth_fixture  # noqa: E402
+from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, library_path  # noqa: E402
+from _fixtures import earth_texels  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--cases", default="10:3840x2160x64,0:1920x1080x64,8:1024x1024x64,9:1920x1080x32")
@@ -27,7 +29,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
 
-earth = load_earth_fixture()
+earth = earth_texels()
 stream = torch.cuda.current_stream().cuda_stream
 for case in a.cases.split(","):
     sid, dims = case.split(":")

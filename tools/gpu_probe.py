@@ -13,17 +13,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
-from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, load_earth_fixture  # noqa: E402
+from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer  # noqa: E402
+from _fixtures import earth_texels  # noqa: E402
 from raytracinginoneweekendincuda_b200 import _abi as A  # noqa: E402
 from oracle import bindings as O  # noqa: E402
 
 OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 res = {"gpu": torch.cuda.get_device_name(0), "cpus": os.cpu_count()}
-earth = load_earth_fixture()
+earth = earth_texels()
 oracle = O.load_oracle()
 
 

@@ -4,8 +4,10 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, load_earth_fixture
-earth = load_earth_fixture()
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer
+from _fixtures import earth_texels  # noqa: E402
+earth = earth_texels()
 for sid in (10, 0, 7, 8, 9):
     sc = BuiltinScene(sid, earth if sid in (2, 9) else None)
     cam = sc.camera(50, 29, 2, 50)  # not a multiple of the tile sizes

@@ -4,11 +4,13 @@ block shape, each checked against the FP64 oracle.  Not part of the test-suite (
 import ctypes as C, os, random, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np
-from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, load_earth_fixture, _abi as A
+from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, _abi as A
+from _fixtures import earth_texels  # noqa: E402
 from oracle import bindings as O
 oracle = O.load_oracle()
-earth = load_earth_fixture()
+earth = earth_texels()
 rnd = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
 t0 = time.time(); n = 0; worst = 1.0; nbad = 0
