@@ -40,10 +40,6 @@ SEED = 1984
 # algorithmic work per ray on the REFERENCE-topology BVH
 FLOP_BOX, FLOP_SPHERE, FLOP_QUAD, FLOP_SHADE = 24.0, 30.0, 28.0, 120.0
 BYTES_NODE = 32.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one RenderMega launch on the 4K frame, from the
-# `ncu --set full` capture summarised in profiles/r1_RenderMega_book1_raw_selected.txt (99.9 MB + 50.3 MB):
-# the fp32 accumulator, read-modify-written once per pixel per launch, whatever the spp.
-NCU_DRAM_BYTES_4K_LAUNCH = 99915520 + 50284800
 
 
 def earth_texels():
@@ -69,6 +65,11 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0)
     ap.add_argument("--upload-flags", type=lambda x: int(x, 0), default=0)
+    ap.add_argument("--single-process", action="store_true",
+                    help="with --gpus N > 1 and no torchrun: ONE process drives the N devices through the C ABI "
+                         "(rt_upload_options.n_devices; reduce inside rt_readback)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -150,22 +151,22 @@ def cpu_baseline(budget_s=12.0):
             "sample": f"{W}x{H}, samples [1,{1 + n}) of {ARGS.spp}, {rays} rays in {dt:.2f} s", "what": what}
 
 
-def gpu_reference():
+def gpu_reference(scene, W, H, spp):
     """The reference's own kernel.cu (FP64, cuRAND XORWOW, -arch=sm_100; oracle/_ref/ref_gpu, built by
     oracle/build_ref.py with argv/ray-counter/event-timing patches) on this GPU, on a bounded sample of the
     workload: the bar of BASELINE.json's ">= 10x the reference's CUDA kernel".  A reported baseline."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu")
+    from oracle import bindings as O
+    exe = O.ref_gpu_path()
     if not os.path.exists(exe):
         return None
-    spp = 8
     try:
-        out = subprocess.run([exe, str(ARGS.width), str(ARGS.height), str(ARGS.scene), str(spp), str(SEED)],
+        out = subprocess.run([exe, str(W), str(H), str(scene), str(spp), str(SEED)],
                              cwd=os.path.dirname(exe), capture_output=True, text=True, timeout=600)
         row = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     except Exception as e:  # noqa: BLE001
         return {"error": str(e)[:200]}
     return {"value": row["mrays_per_s"], "unit": "Mrays/s", "kind": "reference kernel.cu on this GPU (Render only, CUDA events)",
-            "sample": f"{ARGS.width}x{ARGS.height}, {spp} of {ARGS.spp} spp, {row['rays']} rays in {row['render_ms']:.1f} ms",
+            "sample": f"{W}x{H}, {spp} spp, {row['rays']} rays in {row['render_ms']:.1f} ms",
             "render_init_ms": row["render_init_ms"]}
 
 
@@ -199,13 +200,18 @@ def run_reference_arm():
     return 0
 
 
-def workload_config(n):
+def workload_config(n, single=False):
+    if n > 1 and single:
+        par = (f"samples split over {n} GPUs driven by ONE process through the C ABI (rt_upload_options.n_devices); the fp32 "
+               "accumulators are summed on device 0 inside rt_readback")
+    elif n > 1:
+        par = f"samples split over {n} GPU(s), one process each, one NCCL reduce of the fp32 accumulator"
+    else:
+        par = "1 GPU"
     return {"workload": f"{WORKLOAD['name'] if ARGS.scene == 10 else 'scene%d' % ARGS.scene} {ARGS.width}x{ARGS.height} "
                         f"{ARGS.spp}spp max_depth {WORKLOAD['max_depth']}",
             "scene": ARGS.scene, "width": ARGS.width, "height": ARGS.height, "spp": ARGS.spp,
-            "max_depth": WORKLOAD["max_depth"], "seed": SEED,
-            "parallelism": f"samples split over {n} GPU(s), one NCCL reduce of the fp32 accumulator" if n > 1
-            else "1 GPU",
+            "max_depth": WORKLOAD["max_depth"], "seed": SEED, "parallelism": par,
             "l2": "flushed between steps (256 MiB device memset inside the timed region); scene is shared-memory "
                   "resident by design, the 99.5 MB accumulator is written once per pixel per step"}
 
@@ -265,6 +271,99 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ GPU arm
+OTHER_CONFIGS = [  # BASELINE.json configs[2..4] at their image sizes, spp bounded so the whole bench stays within minutes
+    {"name": "configs[2] bouncing spheres (motion blur + checker)", "scene": 0, "width": 1920, "height": 1080, "spp": 64, "of": 512},
+    {"name": "configs[3] Cornell smoke (quads, instances, media)", "scene": 8, "width": 1024, "height": 1024, "spp": 64, "of": 4096},
+    {"name": "configs[4] Book 2 final", "scene": 9, "width": 3840, "height": 2160, "spp": 8, "of": 10000},
+]
+
+
+def flop_per_ray(topo):
+    return FLOP_BOX * topo["n_box"] + FLOP_SPHERE * topo["n_sphere"] + FLOP_QUAD * topo["n_quad"] + FLOP_SHADE
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the shipping kernel, from the committed
+    `ncu --set full` capture (profiles/r2_traffic.json, written by tools/ncu_summary.py): bytes or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            return json.load(f).get(kernel_key, {}).get("dram_bytes")
+    except (OSError, ValueError):
+        return None
+
+
+def time_config(torch, Renderer, sc, cfg, local, peak_tflops, reps=3):
+    """One of the other BASELINE configs on this GPU: CUDA-event time of a launch, roofline with that scene's own
+    reference-topology counts, the reference's kernel.cu on the same frame beside it."""
+    W, H, spp = cfg["width"], cfg["height"], cfg["spp"]
+    cam = sc.camera(W, H, spp, WORKLOAD["max_depth"])
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local))
+    r = Renderer(sc.desc, device=local)
+    r.render(cam, stream=stream)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r.render(cam, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    _, _, st = r.readback(linear=False)
+    info = r.info()
+    r.close()
+    topo = reference_topology_counts(cfg["scene"])
+    fpr = flop_per_ray(topo)
+    achieved = int(st.rays) * fpr / (best * 1e-3) / 1e12
+    out = {"config": cfg["name"], "scene": cfg["scene"], "size": f"{W}x{H}", "spp": spp, "spp_of_config": cfg["of"],
+           "ms": best, "mrays_per_s": int(st.rays) / (best * 1e-3) / 1e6, "rays": int(st.rays),
+           "kernel": {"name": "RenderHitQueue", "features": info.features, "scene_in_smem": info.scene_in_smem,
+                      "block_threads": info.block_threads, "registers": info.registers, "nodes": info.n_nodes},
+           "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                        "frac": achieved / peak_tflops if peak_tflops else None, "flop_per_ray": fpr,
+                        "reference_topology": topo},
+           "timing": "best of %d launches, CUDA events, 256 MiB L2 flush before each" % reps}
+    ref = gpu_reference(cfg["scene"], W, H, 2 if cfg["scene"] == 9 else 4)
+    if ref:
+        out["gpu_reference"] = ref
+    return out
+
+
+def short_frame_e2e(torch, Renderer, local, steps):
+    """BASELINE configs[0] (Book 1 final 1200x675, 10 spp: ~1 ms of kernel) end to end, where upload and readback are
+    not hidden behind a second of rendering: host scene -> rt_scene_upload -> rt_render -> rt_readback of the
+    quantised frame (what the reference writes to its PPM) into host memory."""
+    from raytracinginoneweekendincuda_b200 import BuiltinScene
+    sc = BuiltinScene(10)
+    W, H, spp = 1200, 675, 10
+    cam = sc.camera(W, H, spp, WORKLOAD["max_depth"])
+    parts = {"upload_ms": 0.0, "render_ms": 0.0, "readback_ms": 0.0, "free_ms": 0.0}
+    rays = 0
+    total = 0.0
+    for k in range(steps + 1):
+        t = [time.perf_counter()]
+        rr = Renderer(sc.desc, device=local)
+        t.append(time.perf_counter())
+        rr.render(cam)
+        rr.sync()
+        t.append(time.perf_counter())
+        _, s8, st = rr.readback(linear=False, srgb8=True)
+        t.append(time.perf_counter())
+        rr.close()
+        t.append(time.perf_counter())
+        if k == 0:
+            continue  # warm-up
+        for name, (x, y) in zip(parts, zip(t, t[1:])):
+            parts[name] += (y - x) * 1e3 / steps
+        total += (t[-1] - t[0]) * 1e3 / steps
+        rays = int(st.rays)
+    return {"workload": "book1_final 1200x675 10spp (BASELINE configs[0])", "ms_per_frame": total, "rays": rays,
+            "mrays_per_s": rays / (total * 1e-3) / 1e6, **parts, "h2d_bytes": sc.desc_bytes(), "d2h_bytes": W * H * 3 + 32,
+            "what": "wall clock around upload + render + readback(srgb8) + free, host buffers"}
+
+
 def run_b200_arm():
     import numpy as np
     import torch
@@ -279,6 +378,8 @@ def run_b200_arm():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the render path has no CPU fallback "
                          "(use --impl reference for the host baseline)")
+    single = ARGS.single_process and world == 1 and ARGS.gpus > 1  # one process drives ARGS.gpus devices via the C ABI
+    n_dev = ARGS.gpus if single else world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -308,12 +409,17 @@ def run_b200_arm():
     cam = sc.camera(W, H, spp, WORKLOAD["max_depth"])
     s0, s1 = sample_range(rank, world, spp)
     stream = torch.cuda.current_stream().cuda_stream
-    accum = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)  # caller-owned accumulator (NCCL buffer)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    kw = dict(seed=SEED, stream=stream, accum_ptr=accum.data_ptr(), block_threads=ARGS.block_threads,
-              blocks_per_sm=ARGS.blocks_per_sm, variant=ARGS.variant, flags=ARGS.flags)
-
-    r = Renderer(sc.desc, device=local, upload_flags=ARGS.upload_flags)
+    common = dict(seed=SEED, block_threads=ARGS.block_threads, blocks_per_sm=ARGS.blocks_per_sm, variant=ARGS.variant,
+                  flags=ARGS.flags)
+    if single:
+        accum = None
+        r = Renderer(sc.desc, devices=list(range(n_dev)), upload_flags=ARGS.upload_flags)
+        kw = dict(common)
+    else:
+        accum = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)  # caller-owned accumulator (NCCL buffer)
+        r = Renderer(sc.desc, device=local, upload_flags=ARGS.upload_flags)
+        kw = dict(common, stream=stream, accum_ptr=accum.data_ptr())
     info_desc_bytes = sc.desc_bytes()
 
     def step_resident(time_kernel=None):
@@ -321,6 +427,8 @@ def run_b200_arm():
         if time_kernel is not None:
             time_kernel[0].record()
         r.render(cam, s0, s1, clear=True, **kw)
+        if single:
+            r.readback(linear=False)  # rt_readback: waits for every device, reduces onto device 0
         if time_kernel is not None:
             time_kernel[1].record()
         if world > 1:
@@ -345,18 +453,52 @@ def run_b200_arm():
     _, _, st = r.readback(linear=False)
     rays_rank = torch.tensor([int(st.rays)], dtype=torch.int64, device=dev)  # one step (clear=True resets counters)
     kms = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [kernel_ms]
+    if single:
+        tm = r.timing()
+        per_rank_ms = [float(tm.render_ms[k]) for k in range(tm.n_devices)]
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(kms) for _ in range(world)]
+        dist.all_gather(gathered, kms)
+        per_rank_ms = [float(x.item()) for x in gathered]
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
         rays_all = rays_rank.clone()
         dist.all_reduce(rays_all, op=dist.ReduceOp.SUM)
     else:
         rays_all = rays_rank
-    clk = clocks.stop(world) if rank == 0 else None
+    clk = clocks.stop(n_dev) if rank == 0 else None
     rays_step = int(rays_all.item())
     ms_step = float(ms_total.item()) / ARGS.steps
     value = rays_step / (ms_step * 1e-3) / 1e6
     info = r.info()
+
+    # ---- N ranks: the reduced frame against a 1-GPU render of the same samples, outside the timing
+    nrank_parity = None
+    if (world > 1 or single) and not ARGS.no_parity:
+        if world > 1:
+            accum.zero_()
+            r.render(cam, s0, s1, clear=True, **kw)
+            reduce_accumulators(accum, dst=0)
+            torch.cuda.synchronize()
+            many = accum.clone() if rank == 0 else None
+            dist.barrier(device_ids=[local])
+        else:
+            r.render(cam, s0, s1, clear=True, **kw)
+            lin_many, _, _ = r.readback(linear=True)  # mean radiance, reduced on device 0
+            many = torch.from_numpy(lin_many.reshape(-1)).to(dev) * float(spp)
+        if rank == 0:
+            one = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+            r1 = Renderer(sc.desc, device=local)
+            r1.render(cam, 0, spp, clear=True, seed=SEED, stream=stream, accum_ptr=one.data_ptr(), variant=ARGS.variant)
+            torch.cuda.synchronize()
+            r1.close()
+            diff = (many - one).abs()
+            tol = 3e-6 * one.abs() + 1e-7 * spp
+            nrank_parity = {"allclose_rtol_3e-6": bool((diff <= tol).all().item()),
+                            "max_rel_diff": float((diff / one.abs().clamp_min(1e-3)).max().item()),
+                            "pixels_compared": W * H, "what": f"{n_dev}-GPU reduced sums vs a 1-GPU render of all {spp} samples"}
+            del one, many
     r.close()
 
     # ---- e2e: host description -> upload -> render -> reduce -> linear fp32 frame in pinned host memory
@@ -365,13 +507,15 @@ def run_b200_arm():
         host_frame = torch.empty(H * W * 3, dtype=torch.float32).pin_memory()
         A = sys.modules["raytracinginoneweekendincuda_b200._abi"]
         lib = r.lib
-
         trace = os.environ.get("RT_BENCH_TRACE")
 
         def step_e2e():
             t = [time.perf_counter()]
             flush.zero_()
-            rr = Renderer(sc.desc, device=local, upload_flags=ARGS.upload_flags)  # deep copy + bake + BVH + H2D of every table
+            if single:
+                rr = Renderer(sc.desc, devices=list(range(n_dev)), upload_flags=ARGS.upload_flags)
+            else:
+                rr = Renderer(sc.desc, device=local, upload_flags=ARGS.upload_flags)  # deep copy + bake + BVH + H2D
             t.append(time.perf_counter())
             rr.render(cam, s0, s1, clear=True, **kw)
             if trace:
@@ -381,8 +525,8 @@ def run_b200_arm():
                 reduce_accumulators(accum, dst=0)
             if rank == 0:
                 stt = A.rt_stats()
-                rc = lib.rt_readback(rr._h, C.c_void_p(accum.data_ptr()), C.c_void_p(host_frame.data_ptr()), None,
-                                     C.byref(stt))
+                rc = lib.rt_readback(rr._h, C.c_void_p(accum.data_ptr()) if accum is not None else None,
+                                     C.c_void_p(host_frame.data_ptr()), None, C.byref(stt))
                 assert rc == 0, lib.rt_last_error()
             else:
                 rr.sync()
@@ -406,7 +550,7 @@ def run_b200_arm():
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         ems_step = float(ems.item()) / ARGS.steps
         e2e = {"value": rays_step / (ems_step * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": ems_step,
-               "h2d_bytes_per_step": int(info_desc_bytes) * world, "d2h_bytes_per_step": H * W * 3 * 4 + 32,
+               "h2d_bytes_per_step": int(info_desc_bytes) * n_dev, "d2h_bytes_per_step": H * W * 3 * 4 + 32,
                "what": "rt_scene_upload(host scene) + rt_render + reduce + rt_readback(linear fp32 -> pinned host)"}
         assert float(host_frame[:3 * W].sum()) > 0.0 or rank != 0
 
@@ -416,15 +560,15 @@ def run_b200_arm():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (RenderMega), FP32-issue bound
+    # ---- roofline of the dominant kernel, FP32-issue bound
     topo = reference_topology_counts()
-    flop_ray = FLOP_BOX * topo["n_box"] + FLOP_SPHERE * topo["n_sphere"] + FLOP_QUAD * topo["n_quad"] + FLOP_SHADE
+    flop_ray = flop_per_ray(topo)
     bytes_ray = BYTES_NODE * (topo["n_box"] + topo["n_sphere"] + topo["n_quad"])
     peak = C.c_double()
     sms = C.c_double()
     assert r.lib.rt_measure_fp32_peak(local, C.byref(peak), C.byref(sms)) == 0
-    kernel_ms_max = float(kms.item())
-    rays_kernel = int(rays_rank.item())
+    kernel_ms_max = float(kms.item()) if not single else max(per_rank_ms)
+    rays_kernel = int(rays_rank.item()) if not single else rays_step // n_dev
     achieved = rays_kernel * flop_ray / (kernel_ms_max * 1e-3) / 1e12
     peaks = {}
     try:
@@ -434,16 +578,20 @@ def run_b200_arm():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_bytes = H * W * 3 * 4 * 2  # accumulator read-modify-write, once per pixel per launch
+    kname = {1: "RenderMega", 2: "RenderWave", 3: "RenderHeadTail", 4: "RenderHitQueue"}.get(info.variant, "?")
     roofline = {
-        "bound": "fp32", "kernel": {1: "RenderMega", 2: "RenderWave", 3: "RenderHeadTail", 4: "RenderHitQueue"}.get(info.variant, "?"),
+        "bound": "fp32", "kernel": kname,
         "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
         "frac": achieved / peak.value if peak.value else None,
-        "traffic": NCU_DRAM_BYTES_4K_LAUNCH if (W, H) == (3840, 2160) else None,
+        "traffic": ncu_traffic(f"{kname}<{info.features},{info.scene_in_smem},0>") if (W, H) == (3840, 2160) else None,
+        "traffic_source": "profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this "
+                          "kernel on this frame size (`ncu --set full`); the accumulator's read-modify-write, whatever the spp",
         "peak_source": "FFMA microbenchmark run live on this GPU (rt_measure_fp32_peak); MEASURED_PEAKS.json "
                        "holds only HBM and bf16-tensor peaks, neither of which bounds this path",
         "flop_per_ray": flop_ray, "l1_bytes_per_ray": bytes_ray, "reference_topology": topo,
         "kernel_ms": kernel_ms_max, "rays_per_launch": rays_kernel,
         "grays_per_s_kernel": rays_kernel / (kernel_ms_max * 1e-3) / 1e9,
+        "registers": info.registers, "block_threads": info.block_threads,
         # secondary bound of SURVEY 8(d): node/primitive fetches (algorithmic bytes on the reference topology)
         # against the shared-memory/L1 bandwidth, nominal 128 B/clk/SM at the clock seen during the run
         "l1": {"achieved": rays_kernel * bytes_ray / (kernel_ms_max * 1e-3) / 1e9, "unit": "GB/s",
@@ -455,19 +603,32 @@ def run_b200_arm():
                 "algorithmic_bytes_per_launch": hbm_bytes},
     }
     roofline["l1"]["frac"] = roofline["l1"]["achieved"] / roofline["l1"]["peak"]
+    launches_per_step = n_dev + (1 if single else 0)  # render kernels (+ the reduce/resolve kernel)
     line = {
-        "metric": "Mrays/s incl. secondary rays", "value": value, "unit": "Mrays/s", "n_gpus": world,
+        "metric": "Mrays/s incl. secondary rays", "value": value, "unit": "Mrays/s", "n_gpus": n_dev,
         "steps": ARGS.steps, "warmup": ARGS.warmup, "ms_per_step": ms_step, "ms_per_frame": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(world), "rays_per_frame": rays_step,
-        "clocks": clk, "e2e": e2e, "gpu_launches": ARGS.steps * world + (ARGS.steps * (world + 1) if e2e else 0),
+        "data": "synthetic", "config": workload_config(n_dev, single), "rays_per_frame": rays_step,
+        "clocks": clk, "e2e": e2e,
+        "gpu_launches": ARGS.steps * launches_per_step + ((ARGS.steps + 1) * (launches_per_step + 1) if e2e else 0),
         "kernel": {"features": info.features, "scene_in_smem": info.scene_in_smem, "nodes": info.n_nodes,
-                   "prims": info.n_prims_baked},
+                   "prims": info.n_prims_baked, "registers": info.registers, "block_threads": info.block_threads},
+        "per_rank_kernel_ms": {"min": min(per_rank_ms), "max": max(per_rank_ms), "all": per_rank_ms},
         "roofline": roofline,
     }
-    if world == 1 and not ARGS.no_cpu_baseline:
+    if nrank_parity is not None:
+        line["nrank_parity"] = nrank_parity["allclose_rtol_3e-6"]
+        line["nrank_parity_detail"] = nrank_parity
+    if n_dev == 1 and not ARGS.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
-        line["gpu_reference"] = gpu_reference()
+        line["gpu_reference"] = gpu_reference(ARGS.scene, W, H, 8)
+    if n_dev == 1 and not ARGS.no_configs:
+        cfgs = []
+        for cfg in OTHER_CONFIGS:
+            scn = BuiltinScene(cfg["scene"], earth_texels() if cfg["scene"] in (2, 9) else None)
+            cfgs.append(time_config(torch, Renderer, scn, cfg, local, peak.value))
+        line["configs"] = cfgs
+        line["e2e_short_frame"] = short_frame_e2e(torch, Renderer, local, max(3, ARGS.steps))
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local])
