@@ -768,6 +768,8 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
     const size_t oQuads = ab.Add(packed->quads), oMedia = ab.Add(packed->media), oMaterials = ab.Add(packed->materials);
     const size_t oMatParams = ab.Add(packed->mat_params);
     const size_t oTextures = ab.Add(packed->textures), oPerlins = ab.Add(packed->perlins);
+    const size_t oUvFrames = ab.Add(packed->uv_frames);
+    const size_t oHoisted = ab.Add(std::vector<uint32_t>(packed->hoisted, packed->hoisted + RT_MAX_HOISTED));
     std::vector<DevImage> images(std::max<size_t>(1, packed->image_bytes.size()));
     std::memset(images.data(), 0, images.size() * sizeof(DevImage));
     for (size_t k = 0; k < packed->image_bytes.size(); ++k)
@@ -820,13 +822,14 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
         d.dev.textures = reinterpret_cast<const DevTexture*>(d.arena + oTextures);
         d.dev.perlins = reinterpret_cast<const DevPerlin*>(d.arena + oPerlins);
         d.dev.images = reinterpret_cast<const DevImage*>(d.arena + oImages);
+        d.dev.uv_frames = reinterpret_cast<const DevUvFrame*>(d.arena + oUvFrames);
         d.dev.arena = reinterpret_cast<const uint8_t*>(d.arena);
         d.stats = reinterpret_cast<unsigned long long*>(d.arena + oStats);
         d.tileCounter = reinterpret_cast<unsigned int*>(d.arena + oTile);
         d.debugOut = reinterpret_cast<float*>(d.arena + oDebug);
         d.dev.root_ref = packed->root_ref;
         d.dev.n_hoisted = packed->n_hoisted;
-        for (int j = 0; j < RT_MAX_HOISTED; ++j) d.dev.hoisted[j] = packed->hoisted[j];
+        d.dev.hoisted = reinterpret_cast<const uint32_t*>(d.arena + oHoisted);
         d.dev.n_nodes = (int)packed->nodes.size();
         d.dev.n_spheres = (int)packed->spheres.size();
         d.dev.n_moving = (int)packed->moving.size();

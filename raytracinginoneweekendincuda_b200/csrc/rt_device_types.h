@@ -134,6 +134,16 @@ struct RT_ALIGN(16) DevPerlin {
     uint8_t _p[256];
 };
 
+// ---- UV frame of a sphere baked out of a RotateY chain: the reference takes (u,v) from the OBJECT-space normal
+// (Sphere.h:42-44 inside the instance, Instance.h:136-150 rotates only P and Normal back), so an image-textured sphere
+// under RotateY keeps its texture turned with it.  The accumulated yaw takes the world normal back:
+// x' = c x - s z, z' = s x + c z.  Spheres that need one carry its index + 1 in bits 20..30 of their material word.
+struct DevUvFrame {
+    float s, c;
+};
+#define RT_MATERIAL_INDEX_BITS 20
+#define RT_MATERIAL_INDEX_MASK 0xfffff
+
 // Texels live in the scene arena; the record holds their OFFSET from the arena base, so that the arena is one
 // position-independent block that any device can receive as it is.
 struct RT_ALIGN(16) DevImage {
@@ -161,9 +171,10 @@ struct DevScene {
     const DevTexture* textures;
     const DevPerlin* perlins;
     const DevImage* images;
+    const DevUvFrame* uv_frames;
     const uint8_t* arena; // base of the scene arena (image texel offsets are relative to it)
     uint32_t root_ref;
-    uint32_t hoisted[RT_MAX_HOISTED];
+    const uint32_t* hoisted; // RT_MAX_HOISTED leaf refs in the arena, tested before the tree is entered
     int32_t n_hoisted;
     int32_t n_nodes, n_spheres, n_moving, n_quads, n_media, n_materials, n_textures;
     int32_t features;

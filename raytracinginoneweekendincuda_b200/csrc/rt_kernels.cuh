@@ -92,13 +92,13 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
     sv.textures = scene.textures;
     sv.perlins = scene.perlins;
     sv.images = scene.images;
+    sv.uv_frames = scene.uv_frames;
     sv.arena = scene.arena;
     sv.root_ref = scene.root_ref;
     if constexpr (SMEM)
         if (!(sv.root_ref & RT_REF_LEAF)) sv.root_ref = sv.nodes.a + sv.root_ref * 32u;
     sv.n_hoisted = scene.n_hoisted;
-#pragma unroll
-    for (int k = 0; k < RT_MAX_HOISTED; ++k) sv.hoisted[k] = scene.hoisted[k];
+    sv.hoisted = scene.hoisted;
     return sv;
 }
 

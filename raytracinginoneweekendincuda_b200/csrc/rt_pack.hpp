@@ -57,6 +57,8 @@ struct Baked {
     int material;
     double a[3], b[3], c[3]; // sphere: centre | moving: c0, c1 | quad: Q, u, v
     double radius, time0, time1;
+    double yawSin, yawCos; // accumulated RotateY of the instance chain (object -> world); 0, 1 when there is none
+    bool rotated;
     Box3 box;
 };
 
@@ -83,6 +85,7 @@ struct Packed {
     std::vector<DevMedium> media;
     std::vector<DevMaterial> materials;
     std::vector<double> mat_params;
+    std::vector<DevUvFrame> uv_frames;
     std::vector<DevTexture> textures;
     std::vector<DevPerlin> perlins;
     std::vector<std::vector<uint8_t>> image_bytes;
@@ -120,6 +123,17 @@ inline Baked Bake(const rt_scene_desc& d, const rt_prim& p)
     Baked b;
     std::memset(&b, 0, sizeof b);
     b.box = Box3();
+    b.yawSin = 0.0;
+    b.yawCos = 1.0;
+    for (int k = p.xform_count - 1; k >= 0; --k) { // rotations about one axis compose by adding angles
+        const rt_xform& x = d.xforms[p.first_xform + k];
+        if (x.type != RT_XFORM_ROTATE_Y) continue;
+        const double s = x.v[0], c = x.v[1];
+        const double ns = s * b.yawCos + c * b.yawSin, nc = c * b.yawCos - s * b.yawSin;
+        b.yawSin = ns;
+        b.yawCos = nc;
+        b.rotated = true;
+    }
     b.material = p.material;
     b.radius = p.radius;
     b.time0 = p.time0;
@@ -423,6 +437,30 @@ struct Packer {
 
     Packer(const rt_scene_desc& desc, const rt_upload_options& o) : d(desc), opt(o) {}
 
+    // Does a texture lead to an image (directly or through checkers)?  Only then do (u,v) matter.
+    bool TextureUsesUv(int tex, int depth = 0) const
+    {
+        if (tex < 0 || tex >= d.n_textures || depth > 16) return false;
+        const rt_texture& t = d.textures[tex];
+        if (t.type == RT_TEX_IMAGE) return true;
+        if (t.type == RT_TEX_CHECKER) return TextureUsesUv(t.even, depth + 1) || TextureUsesUv(t.odd, depth + 1);
+        return false;
+    }
+    // Material word of a sphere: the index, plus a UV frame for an image-textured sphere baked out of a RotateY chain.
+    int32_t SphereMaterialWord(const Baked& b)
+    {
+        if (b.material > RT_MATERIAL_INDEX_MASK) throw std::invalid_argument("too many materials");
+        const rt_material& m = d.materials[b.material];
+        const bool textured = m.type != RT_MAT_METAL && m.type != RT_MAT_DIELECTRIC && TextureUsesUv(m.texture);
+        if (!b.rotated || !textured) return b.material;
+        if (out.uv_frames.size() >= 2047) throw std::invalid_argument("too many rotated image-textured spheres");
+        DevUvFrame f;
+        f.s = (float)b.yawSin;
+        f.c = (float)b.yawCos;
+        out.uv_frames.push_back(f);
+        return b.material | (int32_t)(out.uv_frames.size() << RT_MATERIAL_INDEX_BITS);
+    }
+
     void PushSphere(const Baked& b)
     {
         DevSphere s;
@@ -431,7 +469,7 @@ struct Packer {
         s.cz = b.a[2];
         s.radius = b.radius;
         out.spheres.push_back(s);
-        out.sphere_material.push_back(b.material);
+        out.sphere_material.push_back(SphereMaterialWord(b));
     }
     void PushMoving(const Baked& b)
     {
@@ -440,7 +478,7 @@ struct Packer {
         s.c0y = b.a[1];
         s.c0z = b.a[2];
         s.radius = (float)b.radius;
-        s.material = b.material;
+        s.material = SphereMaterialWord(b);
         s.dcx = b.b[0] - b.a[0];
         s.dcy = b.b[1] - b.a[1];
         s.dcz = b.b[2] - b.a[2];
@@ -731,38 +769,83 @@ struct Packer {
         }
         if (b.items.empty()) throw std::invalid_argument("scene has no primitives");
 
-        // Hoisting (SAH mode): an item whose box is most of the scene's box -- Book 1's ground sphere, scene 9's
-        // r = 5000 mist -- gains nothing from a hierarchy: nearly every ray enters its box, so its test would run
-        // inside the divergent leaf path of traversal.  Such items are taken out of the tree and tested up front by
-        // every lane of the warp together; the distance they return then culls the walk through the rest.  The
-        // closest hit is a minimum over all primitives (and medium draws are keyed), so the result does not change.
-        std::vector<int> hoistedItems;
-        if (opt.bvh == RT_BVH_SAH && !(opt.flags & RT_UPLOAD_NO_HOIST) && b.items.size() > 2) {
-            Box3 sceneBox;
-            for (const Item& it : b.items) sceneBox.Grow(it.box);
-            const double sceneArea = sceneBox.Area();
+        // Hoisting (SAH mode).  Three kinds of item gain nothing from the hierarchy and lose a lot inside it, because a
+        // leaf is visited by the few lanes of a warp that happen to reach it in the same step, while an item tested
+        // BEFORE the tree is entered is tested by every lane together, as straight-line code:
+        //   * scene-sized items (Book 1's ground sphere, scene 9's r = 5000 mist): nearly every ray enters their box;
+        //   * every ConstantMedium: its test is two boundary queries plus a logarithm -- by far the longest leaf --
+        //     and ncu put the leaf path of the Cornell-smoke scene on 5.9 of 32 lanes (67 % of its instructions);
+        //   * all surfaces of a tiny scene (<= kFlatMax primitives: the Cornell box has 6 walls): a linear pass over a
+        //     dozen primitives on a full warp costs less than walking a tree on a third of one.
+        // Hoisted items are tested up front and the distance they return then culls the walk through the rest.  The
+        // closest hit is a minimum over all primitives (and medium draws are keyed), so the image does not change.
+        // Slots (RT_MAX_HOISTED): one per medium, one per primitive type of a flattened scene, one per scene-sized item.
+        if (opt.bvh == RT_BVH_SAH && !(opt.flags & RT_UPLOAD_NO_HOIST)) {
+            const int kFlatMax = 16;
+            std::vector<char> take(b.items.size(), 0);
+            int slots = RT_MAX_HOISTED;
+            std::vector<uint32_t> refs;
+            size_t nSurface = 0, nSurfacePrims = 0;
+            bool typePresent[3] = {false, false, false};
+            for (size_t k = 0; k < b.items.size(); ++k)
+                if (b.items[k].type != RT_LEAF_MEDIUM) {
+                    ++nSurface;
+                    nSurfacePrims += runOfItem[k].size();
+                    typePresent[b.items[k].type] = true;
+                }
+            const int nTypes = (int)typePresent[0] + (int)typePresent[1] + (int)typePresent[2];
+            const bool flat = nSurface > 0 && nSurfacePrims <= (size_t)kFlatMax && nTypes <= slots;
+            if (flat) {
+                for (int t = 0; t < 3; ++t) {
+                    if (!typePresent[t]) continue;
+                    std::vector<int> ids;
+                    for (size_t k = 0; k < b.items.size(); ++k)
+                        if (b.items[k].type == t) {
+                            take[k] = 1;
+                            ids.insert(ids.end(), runOfItem[k].begin(), runOfItem[k].end());
+                        }
+                    refs.push_back(EmitRun(t, ids));
+                    --slots;
+                }
+            }
+            for (size_t k = 0; k < b.items.size() && slots > 0; ++k)
+                if (b.items[k].type == RT_LEAF_MEDIUM) {
+                    take[k] = 1;
+                    refs.push_back(RT_REF_MAKE_LEAF(RT_LEAF_MEDIUM, b.items[k].index, 1));
+                    --slots;
+                }
+            if (!flat) {
+                Box3 sceneBox;
+                for (const Item& it : b.items) sceneBox.Grow(it.box);
+                const double sceneArea = sceneBox.Area();
+                size_t left = 0;
+                for (size_t k = 0; k < b.items.size(); ++k) left += take[k] ? 0 : 1;
+                for (size_t k = 0; k < b.items.size() && slots > 0 && left > 2; ++k) {
+                    if (take[k] || !(sceneArea > 0.0 && b.items[k].box.Area() >= 0.5 * sceneArea)) continue;
+                    take[k] = 1;
+                    refs.push_back(EmitRun(b.items[k].type, runOfItem[k]));
+                    --slots;
+                    --left;
+                }
+            }
             std::vector<Item> kept;
             std::vector<std::vector<int>> keptRuns;
-            for (size_t k = 0; k < b.items.size(); ++k) {
-                const bool big = sceneArea > 0.0 && b.items[k].box.Area() >= 0.5 * sceneArea;
-                if (big && (int)hoistedItems.size() < RT_MAX_HOISTED && b.items.size() - hoistedItems.size() > 2) {
-                    hoistedItems.push_back((int)k);
-                } else {
+            for (size_t k = 0; k < b.items.size(); ++k)
+                if (!take[k]) {
                     kept.push_back(b.items[k]);
                     keptRuns.push_back(runOfItem[k]);
                 }
-            }
-            for (int k : hoistedItems) {
-                const Item& it = b.items[k];
-                out.hoisted[out.n_hoisted++] = it.type == RT_LEAF_MEDIUM ? RT_REF_MAKE_LEAF(RT_LEAF_MEDIUM, it.index, 1)
-                                                                         : EmitRun(it.type, runOfItem[k]);
-            }
-            if (!hoistedItems.empty()) {
-                b.items.swap(kept);
-                runOfItem.swap(keptRuns);
-            }
+            for (uint32_t r : refs) out.hoisted[out.n_hoisted++] = r;
+            b.items.swap(kept);
+            runOfItem.swap(keptRuns);
         }
 
+        if (b.items.empty()) { // everything is tested up front: an empty tree (two zeroed records keep the table non-empty)
+            out.nodes.assign(2, DevNode{});
+            out.root_ref = 0xffffffffu; // RT_TRAV_DONE: the walk loop does not run
+            out.max_depth = 0;
+            return;
+        }
         int root;
         if (opt.bvh == RT_BVH_NONE) {
             root = b.BuildList();

@@ -153,9 +153,10 @@ template <bool SMEM> struct SceneView {
     const DevTexture* textures;
     const DevPerlin* perlins;
     const DevImage* images;
+    const DevUvFrame* uv_frames;
     const uint8_t* arena;
     uint32_t root_ref;
-    uint32_t hoisted[RT_MAX_HOISTED]; // leaf refs every ray tests before it enters the tree
+    const uint32_t* hoisted; // leaf refs every ray tests before it enters the tree (global memory: a uniform load)
     int n_hoisted;
 };
 
@@ -372,6 +373,7 @@ struct Hit {
     float u, v;    // quad: alpha, beta; sphere: filled on demand
     bool front;
     int32_t material;
+    int32_t uvFrame; // sphere under a RotateY chain with an image texture: index + 1 into uv_frames, else 0
 };
 
 RT_DEV void SetFaceNormal(Hit& h, const d3& dir, const d3& outward) // Hittable.h:26-30
@@ -442,12 +444,24 @@ RT_DEV void FinalizeSphereAt(d3 c, double radius, const Ray& r, double a, float 
     SetFaceNormal(h, r.d, invR * (h.p - c));
 }
 
+// Material word of a sphere: material index, and (scenes with image textures only) its UV frame above it.
+template <int FEAT> RT_DEV void SetSphereMaterial(Hit& h, int32_t word)
+{
+    if (FEAT & RT_FEAT_TEXTURE_HEAVY) {
+        h.material = word & RT_MATERIAL_INDEX_MASK;
+        h.uvFrame = word >> RT_MATERIAL_INDEX_BITS;
+    } else {
+        h.material = word;
+    }
+}
+
 template <int FEAT, bool SMEM>
 RT_DEV void FinalizeHit(const SceneView<SMEM>& sv, const Ray& r, double a, uint32_t hit, float t, double tMedium, Hit& h)
 {
     const uint32_t type = RT_HIT_TYPE(hit), index = RT_HIT_INDEX(hit);
     h.u = 0.0f;
     h.v = 0.0f;
+    h.uvFrame = 0;
     if ((FEAT & RT_FEAT_MEDIUM) && type == RT_LEAF_MEDIUM) {
         // ConstantMedium.h:86-91: arbitrary normal, front face, phase material
         const float4 m0 = Ld4<SMEM>(sv.media, index * 32u);
@@ -482,12 +496,12 @@ RT_DEV void FinalizeHit(const SceneView<SMEM>& sv, const Ray& r, double a, uint3
         double radius;
         const d3 c = MovingCentre<SMEM>(sv, index, r.time, radius);
         FinalizeSphereAt(c, radius, r, a, t, h);
-        h.material = __double2hiint(LdD2<SMEM>(sv.moving, index * 64u + 16u).y);
+        SetSphereMaterial<FEAT>(h, __double2hiint(LdD2<SMEM>(sv.moving, index * 64u + 16u).y));
     } else {
         double radius;
         const d3 c = SphereCentre<SMEM>(sv, index, radius);
         FinalizeSphereAt(c, radius, r, a, t, h);
-        h.material = LdI<SMEM>(sv.sphere_material, index * 4u);
+        SetSphereMaterial<FEAT>(h, LdI<SMEM>(sv.sphere_material, index * 4u));
     }
 }
 
@@ -497,8 +511,19 @@ RT_DEV void FinalizeHit(const SceneView<SMEM>& sv, const Ray& r, double a, uint3
 // span-1 BVH leaf twice (SURVEY.md trap T2).  Distances are FP64: the scatter
 // point is the origin of the rest of the path.  Returns true with the scatter
 // distance in tOut (always >= tmin > 0).
+// Not inlined: the body holds two boundary queries (each over every primitive type) and is reached from both leaf
+// sites; inlined twice it was ~40 % of the feature-complete kernel's code, and ncu showed that kernel waiting for
+// instruction fetches (stall_no_instruction 5.2 cycles per issue on scene 9).
+#ifndef RT_MEDIUM_INLINE
+#define RT_MEDIUM_INLINE 0 /* build option for the A/B */
+#endif
+#if RT_MEDIUM_INLINE
+#define RT_MEDIUM_FN __device__ __forceinline__
+#else
+#define RT_MEDIUM_FN __device__ __noinline__
+#endif
 template <int FEAT, bool SMEM>
-RT_DEV bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float rcpA, float tminF, float tmaxF,
+RT_MEDIUM_FN bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double a, float rcpA, float tminF, float tmaxF,
                       uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests, double& tOut)
 {
     const float4 m0 = Ld4<SMEM>(sv.media, index * 32u);
@@ -664,9 +689,9 @@ RT_DEV void BeginWalk(const SceneView<SMEM>& sv, const Ray& r, double a, float r
                       uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t slot, uint32_t& primTests)
 {
     tv.Begin(sv.root_ref, stack);
-#pragma unroll
-    for (int k = 0; k < RT_MAX_HOISTED; ++k) // unrolled: the refs stay kernel parameters (constant bank), not a local array
-        if (k < sv.n_hoisted) TestLeaf<FEAT, SMEM>(sv, sv.hoisted[k], r, a, rcpA, tmin, tv, seed, pixel, sample, slot, primTests);
+#pragma unroll 1 // ONE copy of the leaf test here (it is the largest piece of code of the feature-complete kernel)
+    for (int k = 0; k < sv.n_hoisted; ++k)
+        TestLeaf<FEAT, SMEM>(sv, __ldg(&sv.hoisted[k]), r, a, rcpA, tmin, tv, seed, pixel, sample, slot, primTests);
 }
 
 // ----------------------------------------------------------------- textures
@@ -741,7 +766,14 @@ template <int FEAT, bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv,
             const DevImage im = sv.images[idx];
             if (im.height <= 0 || im.width <= 0) return make_f3(0.0f, 1.0f, 1.0f);
             float u = h.u, v = h.v;
-            if (sphereLike) SphereUV(h.outward, u, v);
+            if (sphereLike) {
+                f3 n = h.outward;
+                if (h.uvFrame) { // back to the object space the reference computes (u,v) in
+                    const float fs = __ldg(&sv.uv_frames[h.uvFrame - 1].s), fc = __ldg(&sv.uv_frames[h.uvFrame - 1].c);
+                    n = make_f3(fc * n.x - fs * n.z, n.y, fs * n.x + fc * n.z);
+                }
+                SphereUV(n, u, v);
+            }
             u = fminf(fmaxf(u, 0.0f), 1.0f);
             v = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
             int i = (int)(u * (float)im.width), j = (int)(v * (float)im.height);

@@ -91,3 +91,59 @@ def oracle_render_region(oracle, scene, cam, x0, y0, w, h, s0, s1, seed=1984, bv
                                      threads or (os.cpu_count() or 1), out.ctypes.data, C.byref(st))
     assert rc == 0
     return out, st
+
+
+class HandScene:
+    """A scene description written by hand through the ctypes structs (what a non-C++ host would do): one textured
+    sphere of radius 1, optionally under RotateY(degrees) then Translate(offset) -- the reference's
+    `new Translate(new RotateY(sphere, degrees), offset)`."""
+
+    def __init__(self, earth, degrees=0.0, offset=(0.0, 0.0, 0.0), checker=False):
+        self.earth = np.ascontiguousarray(earth)
+        self.prims = (A.rt_prim * 1)()
+        p = self.prims[0]
+        p.type = A.RT_PRIM_SPHERE
+        p.material = 0
+        p.radius = 1.0
+        p.a[:] = [0.0, 0.0, 0.0]
+        self.xforms = (A.rt_xform * 2)()
+        n_x = 0
+        if degrees != 0.0 or any(offset):
+            self.xforms[0].type = A.RT_XFORM_TRANSLATE  # outermost first
+            self.xforms[0].v[:] = list(offset)
+            self.xforms[1].type = A.RT_XFORM_ROTATE_Y
+            rad = np.radians(degrees)
+            self.xforms[1].v[:] = [float(np.sin(rad)), float(np.cos(rad)), degrees]
+            n_x = 2
+            p.first_xform, p.xform_count = 0, 2
+        self.objects = (A.rt_object * 1)()
+        o = self.objects[0]
+        o.kind = A.RT_OBJ_PRIM
+        o.first_prim, o.prim_count = 0, 1
+        o.bbox[:] = [offset[0] - 1.5, offset[0] + 1.5, offset[1] - 1.0, offset[1] + 1.0, offset[2] - 1.5, offset[2] + 1.5]
+        self.materials = (A.rt_material * 1)()
+        self.materials[0].type = A.RT_MAT_LAMBERTIAN
+        self.materials[0].texture = 2 if checker else 0
+        self.textures = (A.rt_texture * 3)()
+        self.textures[0].type = A.RT_TEX_IMAGE
+        self.textures[0].image = 0
+        self.textures[1].type = A.RT_TEX_SOLID
+        self.textures[1].color[:] = [0.9, 0.1, 0.1]
+        self.textures[2].type = A.RT_TEX_CHECKER  # even = the image, odd = red: (u,v) reached through a checker
+        self.textures[2].even, self.textures[2].odd, self.textures[2].scale = 0, 1, 0.7
+        self.images = (A.rt_image * 1)()
+        self.images[0].width, self.images[0].height = self.earth.shape[1], self.earth.shape[0]
+        self.images[0].rgb = self.earth.ctypes.data_as(C.POINTER(C.c_uint8))
+        self._desc = A.rt_scene_desc(abi_version=A.RT_ABI_VERSION, n_objects=1, n_prims=1, n_xforms=n_x, n_materials=1,
+                                     n_textures=3, n_images=1, objects=self.objects, prims=self.prims, xforms=self.xforms,
+                                     materials=self.materials, textures=self.textures, images=self.images)
+        self.desc = C.pointer(self._desc)
+
+    def camera(self, W, H, spp, max_depth=50):
+        cam = A.rt_camera(image_width=W, image_height=H, samples_per_pixel=spp, max_depth=max_depth, vfov=40.0,
+                          defocus_angle=0.0, focus_dist=1.0, aperture=0.0, time0=0.0, time1=0.0)
+        cam.lookfrom[:] = [0.3, 0.8, 4.0]
+        cam.lookat[:] = [0.3, 0.0, 0.0]
+        cam.vup[:] = [0.0, 1.0, 0.0]
+        cam.background[:] = [0.8, 0.9, 1.0]
+        return cam

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import A
+from conftest import A, HandScene
 from raytracinginoneweekendincuda_b200 import BuiltinScene
 
 
@@ -16,22 +16,25 @@ def pack(lib, desc, bvh=A.RT_BVH_SAH, flags=0, max_leaf=0):
     return rc, info
 
 
-def test_ground_sphere_and_mist_are_hoisted(lib, earth):
-    """Book 1 / scene 0: the r = 1000 ground sphere; scene 9: the r = 5000 mist medium (its box contains the whole
-    scene, reference kernel.cu:481-482).  Cornell scenes have no scene-sized item."""
-    for sid, ref_type in [(10, 0), (0, 0), (9, 3)]:
+def test_hoisting_policy(lib, earth):
+    """What is tested before the tree instead of inside it (csrc/rt_pack.hpp): scene-sized surfaces (Book 1 / scene 0:
+    the r = 1000 ground sphere), every ConstantMedium (scene 9: the blue-glass medium and the r = 5000 mist whose box
+    contains the whole scene, reference kernel.cu:476-482; scene 8: the two smoke boxes), and all surfaces of a tiny
+    scene (scene 8: the six Cornell walls as one run of quads -- its tree is then empty)."""
+    expect = {10: [0], 0: [0], 9: [3, 3], 8: [2, 3, 3], 7: []}  # leaf-ref types: 0 sphere, 2 quad run, 3 medium
+    for sid, types in expect.items():
         sc = BuiltinScene(sid, earth if sid == 9 else None)
         rc, i = pack(lib, sc.desc)
-        assert rc == 0 and i.n_hoisted == 1
-        assert (i.hoisted[0] >> 31) == 1 and ((i.hoisted[0] >> 29) & 3) == ref_type
+        assert rc == 0 and i.n_hoisted == len(types), (sid, i.n_hoisted)
+        for k, t in enumerate(types):
+            assert (i.hoisted[k] >> 31) == 1 and ((i.hoisted[k] >> 29) & 3) == t, (sid, k, hex(i.hoisted[k]))
         rc, j = pack(lib, sc.desc, flags=A.RT_UPLOAD_NO_HOIST)
         assert rc == 0 and j.n_hoisted == 0
-        assert j.n_nodes >= i.n_nodes  # one leaf less in the tree
+        assert j.n_nodes >= i.n_nodes
         assert (i.n_spheres, i.n_moving, i.n_quads, i.n_media) == (j.n_spheres, j.n_moving, j.n_quads, j.n_media)
-    for sid in (7, 8):
-        sc = BuiltinScene(sid)  # (kept alive: the description belongs to it)
-        rc, i = pack(lib, sc.desc)
-        assert rc == 0 and i.n_hoisted == 0
+    sc = BuiltinScene(8)
+    rc, i = pack(lib, sc.desc)
+    assert i.n_nodes == 2 and i.max_depth_bvh == 0 and ((i.hoisted[0] >> 19) & 1023) + 1 == 6  # empty tree, run of 6 quads
 
 
 def test_reference_and_list_modes_never_hoist(lib):
@@ -146,3 +149,16 @@ def test_validation_rejects_unknown_enums_and_null_tables(lib):
     expect_invalid(negative_count, b"negative")
     rc, _ = pack(lib, None)
     assert rc == A.RT_ERR_INVALID
+
+
+def test_rotated_image_textured_sphere_gets_a_uv_frame(lib, earth):
+    """ADVICE r1 (medium): the reference computes sphere (u,v) in OBJECT space (Sphere.h:42-44 inside RotateY::Hit,
+    Instance.h:116-150), so baking a RotateY chain into a sphere must keep its yaw for the texture lookup.  The packer
+    accepts such a scene; rendering parity with the oracle (which moves the ray into object space like the reference)
+    is checked on the GPU in test_parity_gpu.py."""
+    for kw in (dict(degrees=70.0, offset=(0.3, 0.0, 0.0)), dict(degrees=70.0, offset=(0.3, 0.0, 0.0), checker=True),
+               dict()):
+        sc = HandScene(earth, **kw)
+        rc, i = pack(lib, sc.desc)
+        assert rc == 0, lib.rt_last_error()
+        assert i.n_spheres == 1 and i.features & 16  # RT_FEAT_TEXTURE_HEAVY

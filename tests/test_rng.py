@@ -1,10 +1,51 @@
 """The render stream: product (include/rt_rng.h) == oracle restatement, range, known answers."""
 import numpy as np
 
-# (seed, pixel, sample, slot, domain, dim) -> float, fixed when the stream was specified.
+# Known answers: (seed, pixel, sample, slot, domain, dim) -> (32 random bits, uniform).  Computed ONCE from the
+# published hash (PCG4D, Jarzynski & Olano, JCGT 2020, Listing "pcg4d") with the key layout of include/rt_rng.h and
+# cuRAND's bits-to-float (curand_uniform.h:69-72) by the pure-Python restatement below, and frozen here: the render
+# stream is part of the parity contract (every golden render under tests/golden depends on it), so any change to the
+# hash, the key packing or the float conversion must fail this test rather than silently re-key every image.
 KNOWN = [
-    ((1984, 0, 0, 0, 0, 0), None),
+    ((1984, 0, 0, 0, 0, 0), 0x582A4E0D, 0.3443955183029175),
+    ((1984, 0, 0, 0, 0, 1), 0x96DAEA9C, 0.5892779231071472),
+    ((1984, 0, 0, 1, 0, 0), 0x8A3DB156, 0.5400038361549377),
+    ((1984, 8294399, 1023, 50, 0, 7), 0xF4C5F429, 0.9561455249786377),   # last pixel / sample of config 2, bounce 49
+    ((1984, 123456, 77, 3, 5, 0), 0x71FE1BD3, 0.4452836513519287),       # a medium draw (domain 1 + 2*2 + 0)
+    ((1, 2, 3, 4, 0, 5), 0x57D57051, 0.34310057759284973),
+    ((0xFFFFFFFF, 0, 9999, 51, 16, 63), 0x4C26BE39, 0.2974661588668823),
+    ((1984, 4147200, 512, 1, 3, 2), 0x87C45F80, 0.5303401947021484),
 ]
+M32 = 0xFFFFFFFF
+
+
+def pcg4d(x, y, z, w):
+    x, y, z, w = [(v * 1664525 + 1013904223) & M32 for v in (x, y, z, w)]
+    x = (x + y * w) & M32
+    y = (y + z * x) & M32
+    z = (z + x * y) & M32
+    w = (w + y * z) & M32
+    x, y, z, w = [v ^ (v >> 16) for v in (x, y, z, w)]
+    x = (x + y * w) & M32
+    y = (y + z * x) & M32
+    z = (z + x * y) & M32
+    w = (w + y * z) & M32
+    return x, y, z, w
+
+
+def stream_bits(seed, pixel, sample, slot, domain, dim):
+    zword = (slot & 0xFF) | (((dim >> 2) & 0xFF) << 8) | ((domain << 16) & M32)
+    return pcg4d(pixel, sample, zword, seed)[dim & 3]
+
+
+def test_known_answers(lib, oracle):
+    f = np.float32
+    for key, bits, value in KNOWN:
+        assert stream_bits(*key) == bits
+        want = f(bits) * f(2.3283064365386963e-10) + f(1.1641532182693481e-10)
+        assert float(want) == value
+        assert lib.rt_rng_uniform(*key) == value
+        assert oracle.oracle_rng_uniform(*key) == value
 
 
 def test_product_and_oracle_streams_are_identical(lib, oracle):

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Tiny renders of every kernel instantiation, for compute-sanitizer:
+"""Tiny renders of every kernel instantiation (and a two-device handle where there are two GPUs), for compute-sanitizer:
    compute-sanitizer --tool memcheck python tools/sanitize_run.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,7 +11,7 @@ earth = earth_texels()
 for sid in (10, 0, 7, 8, 9):
     sc = BuiltinScene(sid, earth if sid in (2, 9) else None)
     cam = sc.camera(50, 29, 2, 50)  # not a multiple of the tile sizes
-    for variant in (1, 2):
+    for variant in (0, 1, 2, 3, 4):  # AUTO (= hit-queue), megakernel, wavefront, head/tail, hit-queue
         for flags in (0, 0x200, 0x100):  # scene in smem / in global memory / instrumented
             r = Renderer(sc.desc)
             r.render(cam, variant=variant, flags=flags)
