@@ -176,6 +176,15 @@ template <int FEAT> KernelFn PickKernel(int variant, bool smem, bool stats)
 constexpr int kFeatSpheres = 0;
 constexpr int kFeatMotion = RT_FEAT_MOVING | RT_FEAT_TEXTURE;
 constexpr int kFeatAll = RT_FEAT_MOVING | RT_FEAT_QUAD | RT_FEAT_MEDIUM | RT_FEAT_TEXTURE | RT_FEAT_TEXTURE_HEAVY;
+// Cornell-box class (quads + media, solid colours): instantiated for the shipping kernel only -- without the texture
+// and moving-sphere code it is half the size of the feature-complete one.
+constexpr int kFeatBox = RT_FEAT_QUAD | RT_FEAT_MEDIUM;
+
+KernelFn PickHitQueueBox(bool smem, bool stats)
+{
+    if (smem) return stats ? RenderHitQueue<kFeatBox, true, true> : RenderHitQueue<kFeatBox, true, false>;
+    return stats ? RenderHitQueue<kFeatBox, false, true> : RenderHitQueue<kFeatBox, false, false>;
+}
 
 KernelFn PickKernelForFeatures(int features, int variant, bool smem, bool stats, int* picked)
 {
@@ -186,6 +195,10 @@ KernelFn PickKernelForFeatures(int features, int variant, bool smem, bool stats,
     if ((features & ~kFeatMotion) == 0) {
         *picked = kFeatMotion;
         return PickKernel<kFeatMotion>(variant, smem, stats);
+    }
+    if ((features & ~kFeatBox) == 0 && variant == RT_VARIANT_HITQUEUE) {
+        *picked = kFeatBox;
+        return PickHitQueueBox(smem, stats);
     }
     *picked = kFeatAll;
     return PickKernel<kFeatAll>(variant, smem, stats);
@@ -573,7 +586,8 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
     a.materialsBytes = Pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial));
     a.matParamsBytes = Pad16(std::max<size_t>(1, pk.mat_params.size()) * sizeof(double));
 
-    const int featClass = d.dev.features == 0 ? kFeatSpheres : ((d.dev.features & ~kFeatMotion) == 0 ? kFeatMotion : kFeatAll);
+    int featClass = d.dev.features == 0 ? kFeatSpheres : ((d.dev.features & ~kFeatMotion) == 0 ? kFeatMotion : kFeatAll);
+    if (hitQueue && featClass == kFeatAll && (d.dev.features & ~kFeatBox) == 0) featClass = kFeatBox;
     const int maxThreads = wave ? 512 : (queued ? HtMaxThreads(featClass) : MegaMaxThreads(featClass));
     int threads = p->block_threads > 0 ? p->block_threads : maxThreads;
     threads = std::max(32, std::min(maxThreads, (threads / 32) * 32));

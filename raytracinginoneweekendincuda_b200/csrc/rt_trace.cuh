@@ -511,11 +511,14 @@ RT_DEV void FinalizeHit(const SceneView<SMEM>& sv, const Ray& r, double a, uint3
 // span-1 BVH leaf twice (SURVEY.md trap T2).  Distances are FP64: the scatter
 // point is the origin of the rest of the path.  Returns true with the scatter
 // distance in tOut (always >= tmin > 0).
-// Not inlined: the body holds two boundary queries (each over every primitive type) and is reached from both leaf
-// sites; inlined twice it was ~40 % of the feature-complete kernel's code, and ncu showed that kernel waiting for
-// instruction fetches (stall_no_instruction 5.2 cycles per issue on scene 9).
+// The body holds two boundary queries (each over every primitive type) and is reached from both leaf sites: ~40 % of
+// the feature-complete kernel's code, and ncu showed that kernel waiting for instruction fetches
+// (stall_no_instruction 5.2 cycles per issue on scene 9).
+// (Measured, round 2: keeping this body out of line -- one copy instead of two -- shrank the feature-complete kernel
+// from 7 000 to 4 100 instructions but forced the scene view into local memory for the call and lost 20-28 % on
+// scenes 7, 8, 9; the code-size problem is handled by the runtime loop over the hoisted items instead.)
 #ifndef RT_MEDIUM_INLINE
-#define RT_MEDIUM_INLINE 0 /* build option for the A/B */
+#define RT_MEDIUM_INLINE 1 /* build option for the A/B */
 #endif
 #if RT_MEDIUM_INLINE
 #define RT_MEDIUM_FN __device__ __forceinline__

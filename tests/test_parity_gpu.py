@@ -346,7 +346,7 @@ def test_image_textured_sphere_under_rotate_y(oracle, earth, checker):
     assert abs(int(st.rays) - int(ost.rays)) <= 2e-3 * ost.rays
     plain = HandScene(earth, degrees=0.0, offset=(0.3, 0.0, 0.0), checker=checker)
     other, _, _ = gpu_render(plain, cam)
-    assert match_fraction(other, want, spp) < 0.9
+    assert match_fraction(other, want, spp) < 0.95  # (the background pixels agree whatever the texture does)
 
 
 def _ref_gpu(args, env=None, cwd=None):
