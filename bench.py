@@ -434,6 +434,17 @@ def run_b200_arm():
         if world > 1:
             reduce_accumulators(accum, dst=0)
 
+    if single:  # (an NCCL communicator created inside rt_readback prints its banner on stdout as well)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            step_resident()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     for _ in range(max(ARGS.warmup, 0)):
         step_resident()
     barrier()
@@ -488,16 +499,23 @@ def run_b200_arm():
             lin_many, _, _ = r.readback(linear=True)  # mean radiance, reduced on device 0
             many = torch.from_numpy(lin_many.reshape(-1)).to(dev) * float(spp)
         if rank == 0:
+            # the same slices on ONE GPU, accumulated in rank order: what the N accumulators must sum to.  The peer-
+            # memory reduction adds in device order too (bit-identical expected); NCCL may associate differently.
             one = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
             r1 = Renderer(sc.desc, device=local)
-            r1.render(cam, 0, spp, clear=True, seed=SEED, stream=stream, accum_ptr=one.data_ptr(), variant=ARGS.variant)
+            for k in range(n_dev):
+                b0, b1 = sample_range(k, n_dev, spp)
+                r1.render(cam, b0, b1, clear=False, seed=SEED, stream=stream, accum_ptr=one.data_ptr(), variant=ARGS.variant)
             torch.cuda.synchronize()
             r1.close()
             diff = (many - one).abs()
-            tol = 3e-6 * one.abs() + 1e-7 * spp
-            nrank_parity = {"allclose_rtol_3e-6": bool((diff <= tol).all().item()),
-                            "max_rel_diff": float((diff / one.abs().clamp_min(1e-3)).max().item()),
-                            "pixels_compared": W * H, "what": f"{n_dev}-GPU reduced sums vs a 1-GPU render of all {spp} samples"}
+            rel = diff / one.abs().clamp_min(1e-3)
+            ok = bool((diff <= 1e-6 * one.abs() + 1e-7 * spp).all().item())
+            nrank_parity = {"allclose_rtol_1e-6": ok, "max_rel_diff": float(rel.max().item()),
+                            "bit_identical_fraction": float((many == one).float().mean().item()),
+                            "pixels_compared": W * H,
+                            "what": f"{n_dev}-GPU reduced sums vs the same {n_dev} sample slices rendered on 1 GPU and "
+                                    "accumulated in rank order (all pixels of the frame)"}
             del one, many
     r.close()
 
@@ -617,7 +635,7 @@ def run_b200_arm():
         "roofline": roofline,
     }
     if nrank_parity is not None:
-        line["nrank_parity"] = nrank_parity["allclose_rtol_3e-6"]
+        line["nrank_parity"] = nrank_parity["allclose_rtol_1e-6"]
         line["nrank_parity_detail"] = nrank_parity
     if n_dev == 1 and not ARGS.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()

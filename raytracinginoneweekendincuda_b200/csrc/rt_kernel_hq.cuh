@@ -20,7 +20,13 @@
 
 #include "rt_kernels.cuh"
 
+#ifndef RT_HQ_WALK_UNROLL
+#define RT_HQ_WALK_UNROLL 1 /* build option (A/B): two box steps + one leaf step per loop turn (small kernels only) */
+#endif
+
 namespace {
+
+template <int FEAT> constexpr bool kHqWalkUnroll = RT_HQ_WALK_UNROLL != 0 && !(FEAT & RT_FEAT_TEXTURE_HEAVY);
 
 constexpr int kHqQueue = 64; // records per warp: a tail pops 32 before it pushes at most 32; a head needs 32 free
 __host__ __device__ constexpr int HqWarpBytes(int feat)
@@ -54,6 +60,7 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
     const int nTiles = args.tilesX * args.tilesY;
     const f3 background = make_f3(cam.background[0], cam.background[1], cam.background[2]);
     const uint32_t leafMask = (uint32_t)args.megaLeafMask;
+    (void)leafMask;
     unsigned long long nPaths = 0, nNode = 0, nPrim = 0;
 
     while (true) {
@@ -157,6 +164,28 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
                 if (STATS) nPrim += hoistTests;
                 ++nRays;
             }
+            // One turn of the loop = two box steps, then one leaf step.  A lane that reaches a leaf waits for the leaf
+            // step (the FP64 primitive tests then run for every lane that piled up in the two steps before); a lane
+            // that is done (RT_TRAV_DONE has the leaf bit and is excluded) idles until the slowest walk ends.  Same
+            // schedule as the `step & 1` leaf turn of the other kernels, without the step counter and with the loop
+            // test, the reconvergence point and the branch paid once per two box steps instead of once per step.
+            // Measured (4K Book 1 / scene 0 / 7 / 8 / 9, 64 spp): +0.2 / +1.8 / +8.3 / +0.5 / -6.9 % -- a gain wherever the
+            // kernel is small, a loss for the feature-complete instantiation (its code no longer fits the instruction
+            // cache as it is), so that one keeps the plain loop.
+            if constexpr (kHqWalkUnroll<FEAT>) {
+            while (tv.ref != RT_TRAV_DONE) {
+                uint32_t nodeTests = 0, primTests = 0;
+                if (!(tv.ref & RT_REF_LEAF)) TraceBox<SMEM>(sv, slab, 0.001f, stack, tv, nodeTests);
+                if (!(tv.ref & RT_REF_LEAF)) TraceBox<SMEM>(sv, slab, 0.001f, stack, tv, nodeTests);
+                if ((tv.ref & RT_REF_LEAF) && tv.ref != RT_TRAV_DONE)
+                    TraceLeaf<FEAT, SMEM>(sv, ray, a, slab.rcpA, 0.001f, stack, tv, args.seed, pixel, sample, bounce + 1u,
+                                          primTests);
+                if (STATS) {
+                    nNode += nodeTests;
+                    nPrim += primTests;
+                }
+            }
+            } else {
             uint32_t step = 0;
             while (tv.ref != RT_TRAV_DONE) {
                 uint32_t nodeTests = 0, primTests = 0;
@@ -170,6 +199,7 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
                     nNode += nodeTests;
                     nPrim += primTests;
                 }
+            }
             }
             if (walk && tv.hit == RT_HIT_NONE) { // kernel.cu:74-79
                 add = thr * background;
