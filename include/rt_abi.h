@@ -197,8 +197,10 @@ typedef struct rt_upload_options {
 
 enum {
     RT_UPLOAD_NO_HOIST = 1, /* keep scene-sized primitives / media inside the BVH (A/B test of the hoisting) */
-    RT_UPLOAD_REDUCE_NCCL = 2 /* multi-device: sum the accumulators with ncclReduce (libnccl.so.2 is dlopen'ed on
-                                 first use) instead of the fused peer-memory reduce + resolve kernel              */
+    RT_UPLOAD_REDUCE_NCCL = 2, /* multi-device: sum the accumulators with ncclReduce (libnccl.so.2 is dlopen'ed on
+                                  first use) instead of the fused peer-memory reduce + resolve kernel             */
+    RT_UPLOAD_SPLIT_LISTS = 4  /* give every primitive of a small owning list (MakeBox) its own BVH item, as round 1
+                                  did, instead of keeping the list as one leaf (A/B test)                          */
 };
 
 typedef struct rt_render_params {
@@ -218,7 +220,8 @@ typedef struct rt_render_params {
 
 enum {
     RT_FLAG_STATS = 0x100,          /* instrumented kernel: fills rt_stats.paths/node_tests/prim_tests */
-    RT_FLAG_SCENE_IN_GLOBAL = 0x200 /* do not stage the scene in shared memory (A/B test)              */
+    RT_FLAG_SCENE_IN_GLOBAL = 0x200, /* do not stage the scene in shared memory (A/B test)              */
+    RT_FLAG_NODES_IN_GLOBAL = 0x400  /* a scene too large to stage: do not stage its node table either  */
     /* bits 4-5 and 12-30 are development tuning knobs of the kernels (csrc/rt_device.cu)             */
 };
 
@@ -291,6 +294,8 @@ typedef struct rt_scene_info {
     int32_t n_devices;     /* devices the scene is resident on                              */
     int32_t reduce_path;   /* multi-device: 0 = none yet, 1 = peer-memory fused kernel, 2 = NCCL */
     int32_t block_threads, registers; /* launch shape and registers/thread of the last rt_render's kernel */
+    int32_t nodes_in_smem; /* 1 when at least the BVH node table is staged in shared memory           */
+    int32_t _pad;
     uint64_t device_bytes;
     int32_t medium_visits[8]; /* T2: reference-topology visit multiplicity per medium_id */
 } rt_scene_info;

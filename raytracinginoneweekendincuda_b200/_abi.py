@@ -25,8 +25,10 @@ RT_VARIANT_AUTO, RT_VARIANT_MEGAKERNEL, RT_VARIANT_WAVEFRONT, RT_VARIANT_HEADTAI
 RT_BVH_SAH, RT_BVH_REFERENCE, RT_BVH_NONE = 0, 1, 2
 RT_FLAG_STATS = 0x100
 RT_FLAG_SCENE_IN_GLOBAL = 0x200
+RT_FLAG_NODES_IN_GLOBAL = 0x400
 RT_UPLOAD_NO_HOIST = 1
 RT_UPLOAD_REDUCE_NCCL = 2
+RT_UPLOAD_SPLIT_LISTS = 4
 
 D3 = C.c_double * 3
 
@@ -103,7 +105,8 @@ class rt_scene_info(C.Structure):
     _fields_ = [("n_prims_baked", C.c_int32), ("n_nodes", C.c_int32), ("n_media", C.c_int32),
                 ("max_depth_bvh", C.c_int32), ("features", C.c_int32), ("scene_in_smem", C.c_int32),
                 ("variant", C.c_int32), ("n_devices", C.c_int32), ("reduce_path", C.c_int32),
-                ("block_threads", C.c_int32), ("registers", C.c_int32), ("device_bytes", C.c_uint64),
+                ("block_threads", C.c_int32), ("registers", C.c_int32), ("nodes_in_smem", C.c_int32),
+                ("_pad", C.c_int32), ("device_bytes", C.c_uint64),
                 ("medium_visits", C.c_int32 * 8)]
 
 

@@ -417,7 +417,7 @@ struct rt_scene_s {
     int debugPixel = -1, debugSample = -1;
     rt_camera lastCam{};
     bool rendered = false;
-    bool fitsSmem = false;
+    bool fitsSmem = false, nodesInSmem = false;
     int pickedFeatures = 0, pickedVariant = 0, pickedThreads = 0, pickedRegisters = 0;
 };
 
@@ -606,6 +606,20 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
                 break;
             }
     }
+    // a scene that does not fit as a whole: the node table alone, if that fits beside a full-size block
+    bool nodesOnly = false;
+    if (hitQueue && !(p->flags & (RT_FLAG_SCENE_IN_GLOBAL | RT_FLAG_NODES_IN_GLOBAL)) &&
+        (size_t)threads * 4 * stackLevels + (size_t)(threads / 32) * warpBytes + 16 + h->stagedBytes > (size_t)d.maxSmemOptin) {
+        for (int cand = p->block_threads > 0 ? threads : maxThreads; cand >= std::max(512, maxThreads - 128); cand -= 64) {
+            if ((size_t)cand * 4 * stackLevels + (size_t)(cand / 32) * warpBytes + 32 + a.nodesBytes <= (size_t)d.maxSmemOptin) {
+                threads = cand;
+                nodesOnly = true;
+                break;
+            }
+            if (p->block_threads > 0) break;
+        }
+    }
+    a.stageNodesOnly = nodesOnly ? 1 : 0;
     const size_t stackBytes = (size_t)threads * 4 * stackLevels;
     size_t poolBytes = queued ? (size_t)(threads / 32) * warpBytes + 16 : 0;
     if (wave) {
@@ -621,7 +635,7 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
     const bool wantStats = (p->flags & RT_FLAG_STATS) != 0 || a.debugOut != nullptr;
     const bool smem = !(p->flags & RT_FLAG_SCENE_IN_GLOBAL) &&
                       stackBytes + poolBytes + h->stagedBytes <= (size_t)d.maxSmemOptin / (size_t)blocksPerSm;
-    const size_t smemBytes = stackBytes + poolBytes + (smem ? h->stagedBytes : 0);
+    const size_t smemBytes = stackBytes + poolBytes + (smem ? h->stagedBytes : (nodesOnly ? a.nodesBytes + 16 : 0));
     if (smemBytes > (size_t)d.maxSmemOptin) {
         rt_set_error("rt_render: block of %d threads needs %zu B of shared memory (max %d)", threads, smemBytes, d.maxSmemOptin);
         return RT_ERR_INVALID;
@@ -639,6 +653,7 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
     int blocks = d.smCount * blocksPerSm;
     blocks = std::max(1, std::min(blocks, (nTiles + warpsPerBlock - 1) / warpsPerBlock));
     h->fitsSmem = smem;
+    h->nodesInSmem = smem || nodesOnly;
     if (end > begin) {
         fn<<<blocks, threads, smemBytes, stream>>>(d.dev, dc, a);
         RT_CUDA(cudaGetLastError());
@@ -1211,6 +1226,7 @@ int rt_scene_get_info(rt_scene_handle h, rt_scene_info* info)
     info->max_depth_bvh = h->host->max_depth;
     info->features = dev.features;
     info->scene_in_smem = h->fitsSmem ? 1 : 0;
+    info->nodes_in_smem = h->nodesInSmem ? 1 : 0;
     info->variant = h->pickedVariant;
     info->n_devices = (int32_t)h->devs.size();
     info->reduce_path = h->reducePath;

@@ -32,6 +32,7 @@ struct RenderArgs {
     float* debugOut; // [max_depth][8]: hit id, t, material, front, p.x, p.y, p.z, 1
     // byte sizes of the staged arrays (SMEM variant)
     uint32_t nodesBytes, spheresBytes, sphereMatBytes, movingBytes, quadsBytes, mediaBytes, materialsBytes, matParamsBytes;
+    int stageNodesOnly; // scene in global memory, node table staged (SceneView::nodes_shared)
 };
 
 __device__ __forceinline__ uint32_t SmemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -69,6 +70,8 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
                                                       uint32_t& cursor)
 {
     SceneView<SMEM> sv;
+    const uint32_t nodesAt = cursor;
+    (void)nodesAt;
     if constexpr (SMEM) {
         sv.nodes.a = smemBase + StageNodes(cursor, smem, smemBase, scene.nodes, args.nodesBytes);
         sv.spheres.a = smemBase + Stage(cursor, smem, scene.spheres, args.spheresBytes);
@@ -80,6 +83,10 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
         sv.mat_params.a = smemBase + Stage(cursor, smem, scene.mat_params, args.matParamsBytes);
         __syncthreads();
     } else {
+        if (args.stageNodesOnly) {
+            StageNodes(cursor, smem, smemBase, scene.nodes, args.nodesBytes);
+            __syncthreads();
+        }
         sv.nodes.a = reinterpret_cast<const char*>(scene.nodes);
         sv.spheres.a = reinterpret_cast<const char*>(scene.spheres);
         sv.sphere_material.a = reinterpret_cast<const char*>(scene.sphere_material);
@@ -95,8 +102,13 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
     sv.uv_frames = scene.uv_frames;
     sv.arena = scene.arena;
     sv.root_ref = scene.root_ref;
-    if constexpr (SMEM)
+    sv.nodes_shared = false;
+    if constexpr (SMEM) {
         if (!(sv.root_ref & RT_REF_LEAF)) sv.root_ref = sv.nodes.a + sv.root_ref * 32u;
+    } else if (args.stageNodesOnly) {
+        sv.nodes_shared = true; // (the node table was staged first: it starts where the cursor stood on entry)
+        if (!(sv.root_ref & RT_REF_LEAF)) sv.root_ref = smemBase + nodesAt + sv.root_ref * 32u;
+    }
     sv.n_hoisted = scene.n_hoisted;
     sv.hoisted = scene.hoisted;
     return sv;

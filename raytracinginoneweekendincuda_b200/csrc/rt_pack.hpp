@@ -192,6 +192,8 @@ struct Builder {
         }
     }
 
+    static double ItemCost(const Item& it) { return IsectCost(it.type) * std::max(1, it.count); } // (count: prims of a whole list)
+
     int NewLeaf(const std::vector<int>& ids, const Box3& box, int depth = 0)
     {
         // a leaf holds one primitive type, and a medium is always a leaf of its
@@ -244,7 +246,7 @@ struct Builder {
         if (n == 1) return NewLeaf(ids, box, depth);
 
         double leafCost = 0.0;
-        for (int id : ids) leafCost += IsectCost(items[id].type);
+        for (int id : ids) leafCost += ItemCost(items[id]);
 
         const int kBins = 64;
         double bestCost = DBL_MAX;
@@ -265,7 +267,7 @@ struct Builder {
                 int k = (int)(kBins * (c - cbox.lo[axis]) / ext);
                 k = std::min(std::max(k, 0), kBins - 1);
                 bb[k].Grow(items[id].box);
-                bc[k] += IsectCost(items[id].type);
+                bc[k] += ItemCost(items[id]);
                 bn[k]++;
             }
             double rightArea[kBins], rightCost[kBins];
@@ -709,6 +711,7 @@ struct Packer {
         }
 
         // BVH items
+        const int opt_small_list = (opt.flags & RT_UPLOAD_SPLIT_LISTS) ? 0 : 8;
         Builder b;
         b.maxLeaf = opt.max_leaf_prims > 0 ? std::min(opt.max_leaf_prims, 8) : 2;
         const bool perObject = opt.bvh == RT_BVH_REFERENCE || opt.bvh == RT_BVH_NONE;
@@ -732,7 +735,27 @@ struct Packer {
                 ++medIdx;
                 continue;
             }
-            if (!perObject) {
+            // A small owning list of one primitive type (MakeBox: six quads, Instance.h:166-184) stays ONE item: its
+            // primitives share a tight box, so splitting them adds two or three tree levels (and 5x the nodes: scene
+            // 9's ground is 400 such boxes) to save a few primitive tests that then run on fewer lanes.
+            bool wholeList = !perObject && ob.kind == RT_OBJ_LIST && ob.prim_count >= 2 && ob.prim_count <= opt_small_list;
+            for (int k = 1; wholeList && k < ob.prim_count; ++k)
+                wholeList = baked[ob.first_prim + k].type == baked[ob.first_prim].type;
+            if (wholeList) {
+                Item it;
+                it.type = baked[ob.first_prim].type;
+                it.index = ob.first_prim;
+                it.first = 0;
+                it.count = ob.prim_count; // weighs the SAH leaf cost
+                it.box = Box3();
+                std::vector<int> ids;
+                for (int k = 0; k < ob.prim_count; ++k) {
+                    it.box.Grow(baked[ob.first_prim + k].box);
+                    ids.push_back(ob.first_prim + k);
+                }
+                b.items.push_back(it);
+                runOfItem.push_back(ids);
+            } else if (!perObject) {
                 for (int k = 0; k < ob.prim_count; ++k) {
                     Item it;
                     it.type = baked[ob.first_prim + k].type;

@@ -158,6 +158,11 @@ template <bool SMEM> struct SceneView {
     uint32_t root_ref;
     const uint32_t* hoisted; // leaf refs every ray tests before it enters the tree (global memory: a uniform load)
     int n_hoisted;
+    // Scene too large for shared memory as a whole, but its NODE table fits beside the stacks and queues (scene 9
+    // once its 400 boxes are single items: 78 KB): the nodes alone are staged -- traversal steps are then LDS hits
+    // while the primitives still come through L1 -- and refs of internal nodes are shared addresses as in the fully
+    // staged case.  A warp-uniform flag, only looked at by the global-memory instantiations.
+    bool nodes_shared;
 };
 
 // Per-thread traversal stack in shared memory, [level][thread]: entry(level) = base + level*stride, so the lanes of
@@ -533,17 +538,38 @@ RT_MEDIUM_FN bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray
     const uint32_t bref = (uint32_t)__float_as_int(m0.x);
     const uint32_t mediumId = (uint32_t)__float_as_int(m0.z);
     const int visits = __float_as_int(m0.w);
-    const float big = 3.402823466e+38f;
-    float t1f = big;
-    const uint32_t h1 = HitRun<FEAT, SMEM, double>(sv, bref, r, a, rcpA, -1.0e300, t1f, primTests);
-    if (h1 == RT_HIT_NONE) return false;
-    const double t1 = RefineT<FEAT, SMEM>(sv, h1, r, a, t1f);
-    float t2f = big;
-    // the candidates of the second query are fp32 roots: the entry root must not pass
-    // as "beyond t1 + 1e-4" because its fp32 value lies above the refined t1
-    const uint32_t h2 = HitRun<FEAT, SMEM, double>(sv, bref, r, a, rcpA, fmax(t1, (double)t1f) + 0.0001, t2f, primTests);
-    if (h2 == RT_HIT_NONE) return false;
-    const double t2 = RefineT<FEAT, SMEM>(sv, h2, r, a, t2f);
+    double t1, t2;
+    if (RT_REF_TYPE(bref) == RT_LEAF_SPHERE && RT_REF_COUNT(bref) == 1u) {
+        // A single sphere as the boundary (both media of scene 9, kernel.cu:476-482): the two queries of
+        // ConstantMedium.h:60-63 are the two roots of ONE quadratic -- the first over (-inf, inf) returns the smaller
+        // root (Sphere.h:31-38), the second, from t1 + 1e-4, the larger one if it lies beyond.  Solved once, in FP64.
+        double radius;
+        const d3 c = SphereCentre<SMEM>(sv, RT_REF_FIRST(bref), radius);
+        const double ocx = r.o.x - c.x, ocy = r.o.y - c.y, ocz = r.o.z - c.z;
+        const double b = fma(ocx, r.d.x, fma(ocy, r.d.y, ocz * r.d.z));
+        const double cc = fma(ocx, ocx, fma(ocy, ocy, fma(ocz, ocz, -radius * radius)));
+        const double disc = fma(b, b, -a * cc);
+        primTests += 2;
+        if (!(disc > 0.0)) return false;
+        const double sq = SqrtD(disc);
+        const double q = b > 0.0 ? -(b + sq) : (sq - b); // the root pair without cancellation: q/a and cc/q
+        const double ta = q * RcpD(a), tb = cc * RcpD(q);
+        t1 = fmin(ta, tb);
+        t2 = fmax(ta, tb);
+        if (!(t2 > t1 + 0.0001)) return false;
+    } else {
+        const float big = 3.402823466e+38f;
+        float t1f = big;
+        const uint32_t h1 = HitRun<FEAT, SMEM, double>(sv, bref, r, a, rcpA, -1.0e300, t1f, primTests);
+        if (h1 == RT_HIT_NONE) return false;
+        t1 = RefineT<FEAT, SMEM>(sv, h1, r, a, t1f);
+        float t2f = big;
+        // the candidates of the second query are fp32 roots: the entry root must not pass
+        // as "beyond t1 + 1e-4" because its fp32 value lies above the refined t1
+        const uint32_t h2 = HitRun<FEAT, SMEM, double>(sv, bref, r, a, rcpA, fmax(t1, (double)t1f) + 0.0001, t2f, primTests);
+        if (h2 == RT_HIT_NONE) return false;
+        t2 = RefineT<FEAT, SMEM>(sv, h2, r, a, t2f);
+    }
     const double negInvDensity = LdD2<SMEM>(sv.media, index * 32u + 16u).x;
     const double invLength = RsqrtD(a), rayLength = a * invLength;
     double tmax = (double)tmaxF;
@@ -631,6 +657,15 @@ template <> RT_DEV void LoadPair<true>(const SceneView<true>&, uint32_t ref, flo
 }
 template <> RT_DEV void LoadPair<false>(const SceneView<false>& sv, uint32_t ref, float4& lo0, float4& hi0, float4& lo1, float4& hi1)
 {
+    if (sv.nodes_shared) {
+        Base<true> b;
+        b.a = ref; // an address: see SceneView::nodes_shared
+        lo0 = Ld4<true>(b, 0u);
+        hi0 = Ld4<true>(b, 16u);
+        lo1 = Ld4<true>(b, 32u);
+        hi1 = Ld4<true>(b, 48u);
+        return;
+    }
     const uint32_t off = ref * 32u;
     lo0 = Ld4<false>(sv.nodes, off);
     hi0 = Ld4<false>(sv.nodes, off + 16u);
