@@ -87,7 +87,18 @@ def load_cpu_reference():
     earth = None
     if sid in (2, 9):
         earth = earth_texels()
-    lib, flags = O.load_ref_stream(fast=True), "g++ -O3 -march=native"
+    lib, flags = None, "g++ -O3 -march=native"
+    if os.path.exists(O.ref_stream_path(fast=True)):
+        # -march=native was resolved where the library was BUILT; this host may be a different CPU.  Try it in a child
+        # process first (an illegal instruction kills the child, not the bench).
+        probe = ("import ctypes as C, numpy as np, sys; sys.path.insert(0, %r); from oracle import bindings as O; "
+                 "l = O.load_ref_stream(fast=True); o = np.zeros((8, 8, 3)); s = O.ref_stream_stats(); "
+                 "sys.exit(l.ref_stream_render(10, 8, 8, 0, 1, 50, 1984, None, 0, 0, 1, o.ctypes.data, C.byref(s)))" % ROOT)
+        try:
+            if subprocess.run([sys.executable, "-c", probe], capture_output=True, timeout=120).returncode == 0:
+                lib = O.load_ref_stream(fast=True)
+        except Exception:  # noqa: BLE001
+            lib = None
     if lib is None:
         lib, flags = O.load_ref_stream(fast=False), "g++ -O2 -ffp-contract=off (the pin build; no -O3 build present)"
     if lib is not None:

@@ -199,8 +199,8 @@ enum {
     RT_UPLOAD_NO_HOIST = 1, /* keep scene-sized primitives / media inside the BVH (A/B test of the hoisting) */
     RT_UPLOAD_REDUCE_NCCL = 2, /* multi-device: sum the accumulators with ncclReduce (libnccl.so.2 is dlopen'ed on
                                   first use) instead of the fused peer-memory reduce + resolve kernel             */
-    RT_UPLOAD_SPLIT_LISTS = 4  /* give every primitive of a small owning list (MakeBox) its own BVH item, as round 1
-                                  did, instead of keeping the list as one leaf (A/B test)                          */
+    RT_UPLOAD_WHOLE_LISTS = 4  /* keep a small owning list (MakeBox: six quads) as ONE BVH item instead of one item
+                                  per primitive (A/B test: fewer nodes, longer leaves; measured slower)            */
 };
 
 typedef struct rt_render_params {

@@ -28,7 +28,7 @@ RT_FLAG_SCENE_IN_GLOBAL = 0x200
 RT_FLAG_NODES_IN_GLOBAL = 0x400
 RT_UPLOAD_NO_HOIST = 1
 RT_UPLOAD_REDUCE_NCCL = 2
-RT_UPLOAD_SPLIT_LISTS = 4
+RT_UPLOAD_WHOLE_LISTS = 4
 
 D3 = C.c_double * 3
 

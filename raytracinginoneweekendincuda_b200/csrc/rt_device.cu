@@ -412,7 +412,7 @@ struct rt_scene_s {
     uint8_t* hostSrgb[2] = {nullptr, nullptr};
     size_t hostLinearFloats = 0, hostSrgbBytes = 0;
     cudaStream_t copyStream = nullptr; // device 0: progressive device-to-host copies
-    cudaEvent_t evReduce0 = nullptr, evReduce1 = nullptr, evResolve1 = nullptr;
+    cudaEvent_t evReduce0 = nullptr, evReduce1 = nullptr, evResolve1 = nullptr, evReduced = nullptr;
     bool timedReadback = false;
     int debugPixel = -1, debugSample = -1;
     rt_camera lastCam{};
@@ -521,7 +521,7 @@ int QueueReduceResolve(rt_scene_s* h, const float* src, int set, bool linear, bo
     if (multi) {
         // device 0 now holds the total: the partial sums of the others are spent.  Clearing them (after the reduce has
         // read them) keeps "render more samples, reduce again" correct.
-        cudaEvent_t reduced = h->devs[0].evStop; // re-recorded: the next render records it again before anyone waits
+        cudaEvent_t reduced = h->evReduced;
         RT_CUDA(cudaEventRecord(reduced, s0));
         for (int k = 1; k < nDev; ++k) {
             DeviceCtx& d = h->devs[k];
@@ -898,6 +898,7 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
         cudaError_t e = cudaEventCreate(&h->evReduce0);
         if (e == cudaSuccess) e = cudaEventCreate(&h->evReduce1);
         if (e == cudaSuccess) e = cudaEventCreate(&h->evResolve1);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->evReduced, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             rt_set_error("rt_scene_upload: %s", cudaGetErrorString(e));
             rt_scene_free(h);
@@ -1147,8 +1148,6 @@ int rt_get_timing(rt_scene_handle h, rt_timing* out)
         RT_CUDA(cudaEventElapsedTime(&out->reduce_ms, h->evReduce0, h->evReduce1));
         RT_CUDA(cudaEventElapsedTime(&out->resolve_ms, h->evReduce1, h->evResolve1));
     }
-    // (device 0's evStop doubles as the "reduced" marker of a multi-device readback: its render time is only
-    // meaningful before rt_readback, which is when bench.py asks)
     for (size_t k = 0; k < h->devs.size() && k < 16; ++k) {
         DeviceCtx& d = h->devs[k];
         RT_CUDA(cudaSetDevice(d.device));
@@ -1181,6 +1180,7 @@ int rt_scene_free(rt_scene_handle h)
             if (h->evReduce0) cudaEventDestroy(h->evReduce0);
             if (h->evReduce1) cudaEventDestroy(h->evReduce1);
             if (h->evResolve1) cudaEventDestroy(h->evResolve1);
+            if (h->evReduced) cudaEventDestroy(h->evReduced);
         }
     }
     for (NcclComm c : h->comms)

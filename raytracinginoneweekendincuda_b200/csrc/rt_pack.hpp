@@ -711,7 +711,7 @@ struct Packer {
         }
 
         // BVH items
-        const int opt_small_list = (opt.flags & RT_UPLOAD_SPLIT_LISTS) ? 0 : 8;
+        const int opt_small_list = (opt.flags & RT_UPLOAD_WHOLE_LISTS) ? 8 : 0;
         Builder b;
         b.maxLeaf = opt.max_leaf_prims > 0 ? std::min(opt.max_leaf_prims, 8) : 2;
         const bool perObject = opt.bvh == RT_BVH_REFERENCE || opt.bvh == RT_BVH_NONE;
@@ -735,9 +735,10 @@ struct Packer {
                 ++medIdx;
                 continue;
             }
-            // A small owning list of one primitive type (MakeBox: six quads, Instance.h:166-184) stays ONE item: its
-            // primitives share a tight box, so splitting them adds two or three tree levels (and 5x the nodes: scene
-            // 9's ground is 400 such boxes) to save a few primitive tests that then run on fewer lanes.
+            // RT_UPLOAD_WHOLE_LISTS (A/B): a small owning list of one primitive type (MakeBox: six quads,
+            // Instance.h:166-184) stays ONE item -- half the nodes (scene 9: 5 062 -> 2 454, the node table then fits
+            // in shared memory), but every visit tests all six quads one after the other.  Measured slower than
+            // one item per quad: scene 9 4.00 vs 4.19 Grays/s, scene 7 11.6 vs 13.1 (profiles/r2_ab_i.jsonl).
             bool wholeList = !perObject && ob.kind == RT_OBJ_LIST && ob.prim_count >= 2 && ob.prim_count <= opt_small_list;
             for (int k = 1; wholeList && k < ob.prim_count; ++k)
                 wholeList = baked[ob.first_prim + k].type == baked[ob.first_prim].type;

@@ -158,10 +158,10 @@ template <bool SMEM> struct SceneView {
     uint32_t root_ref;
     const uint32_t* hoisted; // leaf refs every ray tests before it enters the tree (global memory: a uniform load)
     int n_hoisted;
-    // Scene too large for shared memory as a whole, but its NODE table fits beside the stacks and queues (scene 9
-    // once its 400 boxes are single items: 78 KB): the nodes alone are staged -- traversal steps are then LDS hits
-    // while the primitives still come through L1 -- and refs of internal nodes are shared addresses as in the fully
-    // staged case.  A warp-uniform flag, only looked at by the global-memory instantiations.
+    // Scene too large for shared memory as a whole, but its NODE table fits beside the stacks and queues: the nodes
+    // alone are staged -- traversal steps are then LDS hits while the primitives still come through L1 -- and refs of
+    // internal nodes are shared addresses as in the fully staged case.  A warp-uniform flag, only looked at by the
+    // global-memory instantiations.  (Measured on scene 9 built with RT_UPLOAD_WHOLE_LISTS, 78 KB of nodes: +1.8 %.)
     bool nodes_shared;
 };
 
