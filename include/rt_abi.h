@@ -199,8 +199,10 @@ enum {
     RT_UPLOAD_NO_HOIST = 1, /* keep scene-sized primitives / media inside the BVH (A/B test of the hoisting) */
     RT_UPLOAD_REDUCE_NCCL = 2, /* multi-device: sum the accumulators with ncclReduce (libnccl.so.2 is dlopen'ed on
                                   first use) instead of the fused peer-memory reduce + resolve kernel             */
-    RT_UPLOAD_WHOLE_LISTS = 4  /* keep a small owning list (MakeBox: six quads) as ONE BVH item instead of one item
+    RT_UPLOAD_WHOLE_LISTS = 4, /* keep a small owning list (MakeBox: six quads) as ONE BVH item instead of one item
                                   per primitive (A/B test: fewer nodes, longer leaves; measured slower)            */
+    RT_UPLOAD_NO_BOXES = 8     /* do not recognise closed six-quad boxes (MakeBox, Instance.h:166-184): test their
+                                  quads one by one as the reference does (A/B test of the slab-tested box)          */
 };
 
 typedef struct rt_render_params {
@@ -308,8 +310,10 @@ typedef struct rt_pack_info {
     int32_t max_depth_bvh; /* levels the traversal stack must hold (joins of mixed leaves included) */
     int32_t features;      /* RT_FEAT_* */
     int32_t n_hoisted;     /* scene-sized items tested before the tree (see RT_UPLOAD_NO_HOIST) */
-    uint32_t hoisted[4];   /* their leaf refs: type in bits 30..29 (0 sphere, 1 moving, 2 quad, 3 medium) */
+    uint32_t hoisted[4];   /* their leaf refs: type in bits 30..28 (0 sphere, 1 moving, 2 quad, 3 medium, 4 box) */
     uint64_t staged_bytes; /* nodes + primitives + materials: what a CTA stages in shared memory when it fits */
+    int32_t n_boxes;       /* closed six-quad boxes tested by one slab test (their quads are counted in n_quads) */
+    int32_t _pad;
 } rt_pack_info;
 int rt_scene_pack_info(const rt_scene_desc* scene, const rt_upload_options* opt, rt_pack_info* out);
 

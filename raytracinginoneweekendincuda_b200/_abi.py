@@ -29,6 +29,7 @@ RT_FLAG_NODES_IN_GLOBAL = 0x400
 RT_UPLOAD_NO_HOIST = 1
 RT_UPLOAD_REDUCE_NCCL = 2
 RT_UPLOAD_WHOLE_LISTS = 4
+RT_UPLOAD_NO_BOXES = 8
 
 D3 = C.c_double * 3
 
@@ -123,7 +124,7 @@ class rt_pack_info(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_spheres", C.c_int32), ("n_moving", C.c_int32), ("n_quads", C.c_int32),
                 ("n_media", C.c_int32), ("n_materials", C.c_int32), ("n_mat_params", C.c_int32),
                 ("max_depth_bvh", C.c_int32), ("features", C.c_int32), ("n_hoisted", C.c_int32),
-                ("hoisted", C.c_uint32 * 4), ("staged_bytes", C.c_uint64)]
+                ("hoisted", C.c_uint32 * 4), ("staged_bytes", C.c_uint64), ("n_boxes", C.c_int32), ("_pad", C.c_int32)]
 
 
 def declare_host(lib: C.CDLL) -> None:

@@ -369,6 +369,7 @@ uint32_t StagedBytes(const rtpack::Packed& pk)
            Pad16(std::max<size_t>(1, pk.sphere_material.size()) * sizeof(int32_t)) +
            Pad16(std::max<size_t>(1, pk.moving.size()) * sizeof(DevMovingSphere)) +
            Pad16(std::max<size_t>(1, pk.quads.size()) * sizeof(DevQuad)) +
+           Pad16(std::max<size_t>(1, pk.boxes.size()) * sizeof(DevBox)) +
            Pad16(std::max<size_t>(1, pk.media.size()) * sizeof(DevMedium)) +
            Pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial)) +
            Pad16(std::max<size_t>(1, pk.mat_params.size()) * sizeof(double));
@@ -582,6 +583,7 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
     a.sphereMatBytes = Pad16(std::max<size_t>(1, pk.sphere_material.size()) * sizeof(int32_t));
     a.movingBytes = Pad16(std::max<size_t>(1, pk.moving.size()) * sizeof(DevMovingSphere));
     a.quadsBytes = Pad16(std::max<size_t>(1, pk.quads.size()) * sizeof(DevQuad));
+    a.boxesBytes = Pad16(std::max<size_t>(1, pk.boxes.size()) * sizeof(DevBox));
     a.mediaBytes = Pad16(std::max<size_t>(1, pk.media.size()) * sizeof(DevMedium));
     a.materialsBytes = Pad16(std::max<size_t>(1, pk.materials.size()) * sizeof(DevMaterial));
     a.matParamsBytes = Pad16(std::max<size_t>(1, pk.mat_params.size()) * sizeof(double));
@@ -592,7 +594,8 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
     int threads = p->block_threads > 0 ? p->block_threads : maxThreads;
     threads = std::max(32, std::min(maxThreads, (threads / 32) * 32));
     int blocksPerSm = p->blocks_per_sm > 0 ? p->blocks_per_sm : 1;
-    const int stackLevels = std::max(3, std::min(kMaxStackLevels, h->host->max_depth + 3)); // + sentinel slot
+    // + sentinel slot; at least the hoisted refs + root + sentinel (BeginWalkStacked parks them there before the tree)
+    const int stackLevels = std::max(RT_MAX_HOISTED + 2, std::min(kMaxStackLevels, h->host->max_depth + 3));
     a.stackLevels = stackLevels;
     if (wave) blocksPerSm = 1;
     const size_t warpBytes = hitQueue ? HqWarpBytes(featClass) : HtWarpBytes(featClass);
@@ -723,6 +726,7 @@ int rt_scene_pack_info(const rt_scene_desc* scene, const rt_upload_options* opt,
         out->n_spheres = (int32_t)p.spheres.size();
         out->n_moving = (int32_t)p.moving.size();
         out->n_quads = (int32_t)p.quads.size();
+        out->n_boxes = (int32_t)p.boxes.size();
         out->n_media = (int32_t)p.media.size();
         out->n_materials = (int32_t)p.materials.size();
         out->n_mat_params = (int32_t)p.mat_params.size();
@@ -794,7 +798,8 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
     ArenaBuilder ab;
     const size_t oNodes = ab.Add(packed->nodes), oSpheres = ab.Add(packed->spheres);
     const size_t oSphereMat = ab.Add(packed->sphere_material), oMoving = ab.Add(packed->moving);
-    const size_t oQuads = ab.Add(packed->quads), oMedia = ab.Add(packed->media), oMaterials = ab.Add(packed->materials);
+    const size_t oQuads = ab.Add(packed->quads), oBoxes = ab.Add(packed->boxes);
+    const size_t oMedia = ab.Add(packed->media), oMaterials = ab.Add(packed->materials);
     const size_t oMatParams = ab.Add(packed->mat_params);
     const size_t oTextures = ab.Add(packed->textures), oPerlins = ab.Add(packed->perlins);
     const size_t oUvFrames = ab.Add(packed->uv_frames);
@@ -845,6 +850,7 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
         d.dev.sphere_material = reinterpret_cast<const int32_t*>(d.arena + oSphereMat);
         d.dev.moving = reinterpret_cast<const DevMovingSphere*>(d.arena + oMoving);
         d.dev.quads = reinterpret_cast<const DevQuad*>(d.arena + oQuads);
+        d.dev.boxes = reinterpret_cast<const DevBox*>(d.arena + oBoxes);
         d.dev.media = reinterpret_cast<const DevMedium*>(d.arena + oMedia);
         d.dev.materials = reinterpret_cast<const DevMaterial*>(d.arena + oMaterials);
         d.dev.mat_params = reinterpret_cast<const double*>(d.arena + oMatParams);
@@ -863,6 +869,7 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
         d.dev.n_spheres = (int)packed->spheres.size();
         d.dev.n_moving = (int)packed->moving.size();
         d.dev.n_quads = (int)packed->quads.size();
+        d.dev.n_boxes = (int)packed->boxes.size();
         d.dev.n_media = (int)packed->media.size();
         d.dev.n_materials = (int)packed->materials.size();
         d.dev.n_textures = (int)packed->textures.size();

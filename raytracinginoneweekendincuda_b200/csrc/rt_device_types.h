@@ -35,22 +35,23 @@ struct RT_ALIGN(16) DevNode {
 
 // ref encoding.  Internal: index of the first of its two children.  Leaf:
 //   bit 31      = 1
-//   bits 30..29 = primitive type (RT_LEAF_*)
-//   bits 28..19 = count-1 (1..1024 primitives)
-//   bits 18..0  = first index in that type's array
+//   bits 30..28 = leaf type (RT_LEAF_*)
+//   bits 27..18 = count-1 (1..1024 records)
+//   bits 17..0  = first index in that type's array
 #define RT_REF_LEAF 0x80000000u
 #define RT_LEAF_SPHERE 0u
 #define RT_LEAF_MOVING 1u
 #define RT_LEAF_QUAD 2u
 #define RT_LEAF_MEDIUM 3u
-#define RT_REF_TYPE(r) (((r) >> 29) & 3u)
-#define RT_REF_COUNT(r) ((((r) >> 19) & 1023u) + 1u)
-#define RT_REF_FIRST(r) ((r)&0x7ffffu)
+#define RT_LEAF_BOX 4u /* a closed six-quad box (DevBox); its hits are reported as hits of its quads */
+#define RT_REF_TYPE(r) (((r) >> 28) & 7u)
+#define RT_REF_COUNT(r) ((((r) >> 18) & 1023u) + 1u)
+#define RT_REF_FIRST(r) ((r)&0x3ffffu)
 #define RT_REF_MAKE_LEAF(type, first, count) \
-    (RT_REF_LEAF | ((uint32_t)(type) << 29) | (((uint32_t)(count)-1u) << 19) | (uint32_t)(first))
+    (RT_REF_LEAF | ((uint32_t)(type) << 28) | (((uint32_t)(count)-1u) << 18) | (uint32_t)(first))
 #define RT_MAX_LEAF_PRIMS 1024
 #define RT_MAX_HOISTED 4 /* leaf refs tested before the tree is entered (rt_pack.hpp: hoisting) */
-#define RT_MAX_PRIMS_PER_TYPE (1 << 19)
+#define RT_MAX_PRIMS_PER_TYPE (1 << 18)
 
 // Hit identifier carried out of traversal: type in bits 30..29, index below.
 #define RT_HIT_NONE 0xffffffffu
@@ -87,6 +88,19 @@ struct RT_ALIGN(16) DevQuad {
     float ux, uy, uz;
     float vx, vy, vz;
     int32_t material;
+};
+
+// ---- Box: the six quads MakeBox builds (reference Instance.h:166-184), possibly under Translate / RotateY -- any
+// closed parallelepiped of six quads.  128 bytes.  The reference tests the six quads one after the other
+// (HittableList.h:39-57); a line meets a convex box in at most two of them, the entry and the exit of the three
+// slabs, so ONE slab test over the three pairs of parallel faces finds the face that the six tests would find:
+// pair p has the unit normal n[p] and its two faces lie at n[p].x = lo[p] < hi[p].  A hit is reported as a hit
+// of the face's own DevQuad (first_quad + face number), which is what FinalizeHit refines and shades.
+struct RT_ALIGN(16) DevBox {
+    double n[3][3];
+    double lo[3], hi[3];
+    uint32_t first_quad; // the six quads, contiguous in DevScene.quads
+    uint32_t faces;      // 3 bits per slab face: quad number (0..5) of pair p's lo face at bits 6p, hi face at 6p+3
 };
 
 // ---- ConstantMedium (reference ConstantMedium.h:18-50): 32 bytes.
@@ -165,6 +179,7 @@ struct DevScene {
     const int32_t* sphere_material;
     const DevMovingSphere* moving;
     const DevQuad* quads;
+    const DevBox* boxes;
     const DevMedium* media;
     const DevMaterial* materials;
     const double* mat_params; // metal fuzz / dielectric index of refraction, FP64
@@ -176,7 +191,7 @@ struct DevScene {
     uint32_t root_ref;
     const uint32_t* hoisted; // RT_MAX_HOISTED leaf refs in the arena, tested before the tree is entered
     int32_t n_hoisted;
-    int32_t n_nodes, n_spheres, n_moving, n_quads, n_media, n_materials, n_textures;
+    int32_t n_nodes, n_spheres, n_moving, n_quads, n_boxes, n_media, n_materials, n_textures;
     int32_t features;
 };
 

@@ -21,12 +21,22 @@
 #include "rt_kernels.cuh"
 
 #ifndef RT_HQ_WALK_UNROLL
-#define RT_HQ_WALK_UNROLL 1 /* build option (A/B): two box steps + one leaf step per loop turn (small kernels only) */
+#define RT_HQ_WALK_UNROLL 1 /* build option (A/B): two box steps + one leaf step per loop turn: 0 never, 1 small kernels, 2 all */
 #endif
 
 namespace {
 
-template <int FEAT> constexpr bool kHqWalkUnroll = RT_HQ_WALK_UNROLL != 0 && !(FEAT & RT_FEAT_TEXTURE_HEAVY);
+template <int FEAT> constexpr bool kHqWalkUnroll = RT_HQ_WALK_UNROLL == 2 || (RT_HQ_WALK_UNROLL == 1 && !(FEAT & RT_FEAT_TEXTURE_HEAVY));
+
+#ifndef RT_HQ_STACKED_HOIST
+#define RT_HQ_STACKED_HOIST 1 /* build option (A/B): hoisted items through the walk loop's leaf step (BeginWalkStacked):
+                                 0 never, 1 the feature-complete kernel, 2 every kernel */
+#endif
+// Measured (64 spp; Book 1 4K / scene 0 / 7 / 8 / 9, Grays/s): never 21.24 / 14.33 / 17.59 / 12.97 / 4.59; every kernel
+// 20.84 / 14.33 / 17.38 / 12.87 / 4.97 (profiles/r2_ab_p.jsonl).  The feature-complete kernel shrinks from 5 344 to
+// 4 048 instructions and gains 8 %; the small kernels lose 1-2 % to the extra loop turns.
+template <int FEAT>
+constexpr bool kHqStackedHoist = RT_HQ_STACKED_HOIST == 2 || (RT_HQ_STACKED_HOIST == 1 && (FEAT & RT_FEAT_TEXTURE_HEAVY) != 0);
 
 constexpr int kHqQueue = 64; // records per warp: a tail pops 32 before it pushes at most 32; a head needs 32 free
 __host__ __device__ constexpr int HqWarpBytes(int feat)
@@ -159,9 +169,14 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
             if (walk) {
                 slab = MakeSlab(ray);
                 a = fma(ray.d.x, ray.d.x, fma(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
-                uint32_t hoistTests = 0;
-                BeginWalk<FEAT, SMEM>(sv, ray, a, slab.rcpA, 0.001f, stack, tv, args.seed, pixel, sample, bounce + 1u, hoistTests);
-                if (STATS) nPrim += hoistTests;
+                if constexpr (kHqStackedHoist<FEAT>) {
+                    BeginWalkStacked<SMEM>(sv, stack, tv);
+                } else {
+                    uint32_t hoistTests = 0;
+                    BeginWalk<FEAT, SMEM>(sv, ray, a, slab.rcpA, 0.001f, stack, tv, args.seed, pixel, sample, bounce + 1u,
+                                          hoistTests);
+                    if (STATS) nPrim += hoistTests;
+                }
                 ++nRays;
             }
             // One turn of the loop = two box steps, then one leaf step.  A lane that reaches a leaf waits for the leaf

@@ -31,7 +31,7 @@ struct RenderArgs {
     int debugPixel, debugSample;
     float* debugOut; // [max_depth][8]: hit id, t, material, front, p.x, p.y, p.z, 1
     // byte sizes of the staged arrays (SMEM variant)
-    uint32_t nodesBytes, spheresBytes, sphereMatBytes, movingBytes, quadsBytes, mediaBytes, materialsBytes, matParamsBytes;
+    uint32_t nodesBytes, spheresBytes, sphereMatBytes, movingBytes, quadsBytes, boxesBytes, mediaBytes, materialsBytes, matParamsBytes;
     int stageNodesOnly; // scene in global memory, node table staged (SceneView::nodes_shared)
 };
 
@@ -78,6 +78,7 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
         sv.sphere_material.a = smemBase + Stage(cursor, smem, scene.sphere_material, args.sphereMatBytes);
         sv.moving.a = smemBase + Stage(cursor, smem, scene.moving, args.movingBytes);
         sv.quads.a = smemBase + Stage(cursor, smem, scene.quads, args.quadsBytes);
+        sv.boxes.a = smemBase + Stage(cursor, smem, scene.boxes, args.boxesBytes);
         sv.media.a = smemBase + Stage(cursor, smem, scene.media, args.mediaBytes);
         sv.materials.a = smemBase + Stage(cursor, smem, scene.materials, args.materialsBytes);
         sv.mat_params.a = smemBase + Stage(cursor, smem, scene.mat_params, args.matParamsBytes);
@@ -92,6 +93,7 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
         sv.sphere_material.a = reinterpret_cast<const char*>(scene.sphere_material);
         sv.moving.a = reinterpret_cast<const char*>(scene.moving);
         sv.quads.a = reinterpret_cast<const char*>(scene.quads);
+        sv.boxes.a = reinterpret_cast<const char*>(scene.boxes);
         sv.media.a = reinterpret_cast<const char*>(scene.media);
         sv.materials.a = reinterpret_cast<const char*>(scene.materials);
         sv.mat_params.a = reinterpret_cast<const char*>(scene.mat_params);

@@ -64,7 +64,7 @@ struct Baked {
 
 // Something the BVH treats as one leaf entry.
 struct Item {
-    int type;  // RT_LEAF_*
+    int type;  // RT_LEAF_* (RT_LEAF_BOX: six baked quads that form a closed box, tested as one DevBox)
     int index; // SAH: index into baked[] (or media[] for RT_LEAF_MEDIUM)
     int first, count; // REFERENCE/LIST: run of baked prims (all of `type`)
     Box3 box;
@@ -82,6 +82,7 @@ struct Packed {
     std::vector<int32_t> sphere_material; // parallel to spheres: read once per ray, after traversal
     std::vector<DevMovingSphere> moving;
     std::vector<DevQuad> quads;
+    std::vector<DevBox> boxes;
     std::vector<DevMedium> media;
     std::vector<DevMaterial> materials;
     std::vector<double> mat_params;
@@ -188,18 +189,20 @@ struct Builder {
         case RT_LEAF_SPHERE: return 1.5;
         case RT_LEAF_MOVING: return 1.8;
         case RT_LEAF_QUAD: return 1.3;
+        case RT_LEAF_BOX: return 2.5;
         default: return 12.0;
         }
     }
 
     static double ItemCost(const Item& it) { return IsectCost(it.type) * std::max(1, it.count); } // (count: prims of a whole list)
+    static constexpr int kSurfaceTypes[4] = {RT_LEAF_SPHERE, RT_LEAF_MOVING, RT_LEAF_QUAD, RT_LEAF_BOX};
 
     int NewLeaf(const std::vector<int>& ids, const Box3& box, int depth = 0)
     {
         // a leaf holds one primitive type, and a medium is always a leaf of its
         // own; mixed sets are chained through internal nodes sharing `box`
         std::vector<std::vector<int>> groups;
-        for (int t = 0; t < 3; ++t) {
+        for (int t : kSurfaceTypes) {
             std::vector<int> g;
             for (int id : ids)
                 if (items[id].type == t) g.push_back(id);
@@ -518,9 +521,117 @@ struct Packer {
         out.quads.push_back(q);
     }
 
-    // Appends baked prims [ids] (one type) to the device arrays; returns a leaf ref.
+    // Six baked quads = a closed box?  (MakeBox, Instance.h:166-184, under any Translate / RotateY chain; any closed
+    // parallelepiped of six quads qualifies.)  The faces must pair up into three pairs with parallel normals, the three
+    // normals must span space, and the 24 corners must be 8 points shared by three faces each.  Fills the slab record.
+    bool MakeDevBox(const int* ids, DevBox& box) const
+    {
+        double nrm[6][3], corners[24][3];
+        double scale = 0.0;
+        for (int k = 0; k < 6; ++k) {
+            const Baked& q = baked[ids[k]];
+            if (q.type != RT_LEAF_QUAD) return false;
+            const double* u = q.b;
+            const double* v = q.c;
+            const double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+            const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            if (!(len > 0.0)) return false;
+            for (int a = 0; a < 3; ++a) {
+                nrm[k][a] = n[a] / len;
+                corners[4 * k][a] = q.a[a];
+                corners[4 * k + 1][a] = q.a[a] + u[a];
+                corners[4 * k + 2][a] = q.a[a] + v[a];
+                corners[4 * k + 3][a] = q.a[a] + u[a] + v[a];
+                scale = std::max(scale, std::max(std::fabs(u[a]), std::fabs(v[a])));
+            }
+        }
+        const double eps = 1e-9 * scale;
+        // 8 distinct corners, each on three faces
+        double pts[8][3];
+        int uses[8], nPts = 0;
+        for (int c = 0; c < 24; ++c) {
+            int at = -1;
+            for (int k = 0; k < nPts && at < 0; ++k)
+                if (std::fabs(pts[k][0] - corners[c][0]) <= eps && std::fabs(pts[k][1] - corners[c][1]) <= eps &&
+                    std::fabs(pts[k][2] - corners[c][2]) <= eps)
+                    at = k;
+            if (at < 0) {
+                if (nPts == 8) return false;
+                for (int a = 0; a < 3; ++a) pts[nPts][a] = corners[c][a];
+                uses[nPts] = 0;
+                at = nPts++;
+            }
+            ++uses[at];
+        }
+        if (nPts != 8) return false;
+        for (int k = 0; k < 8; ++k)
+            if (uses[k] != 3) return false;
+        // three pairs of parallel faces
+        int partner[6] = {-1, -1, -1, -1, -1, -1};
+        int pairFirst[3], nPairs = 0;
+        for (int k = 0; k < 6; ++k) {
+            if (partner[k] >= 0) continue;
+            for (int j = k + 1; j < 6 && partner[k] < 0; ++j) {
+                if (partner[j] >= 0) continue;
+                const double c = nrm[k][0] * nrm[j][0] + nrm[k][1] * nrm[j][1] + nrm[k][2] * nrm[j][2];
+                if (std::fabs(c) > 1.0 - 1e-12) {
+                    partner[k] = j;
+                    partner[j] = k;
+                }
+            }
+            if (partner[k] < 0 || nPairs == 3) return false;
+            pairFirst[nPairs++] = k;
+        }
+        if (nPairs != 3) return false;
+        const double* n0 = nrm[pairFirst[0]];
+        const double* n1 = nrm[pairFirst[1]];
+        const double* n2 = nrm[pairFirst[2]];
+        const double det = n0[0] * (n1[1] * n2[2] - n1[2] * n2[1]) - n0[1] * (n1[0] * n2[2] - n1[2] * n2[0]) +
+                           n0[2] * (n1[0] * n2[1] - n1[1] * n2[0]);
+        if (!(std::fabs(det) > 1e-6)) return false;
+        std::memset(&box, 0, sizeof box);
+        for (int p = 0; p < 3; ++p) {
+            const int k = pairFirst[p], j = partner[k];
+            const double* n = nrm[k];
+            const double dk = n[0] * baked[ids[k]].a[0] + n[1] * baked[ids[k]].a[1] + n[2] * baked[ids[k]].a[2];
+            const double dj = n[0] * baked[ids[j]].a[0] + n[1] * baked[ids[j]].a[1] + n[2] * baked[ids[j]].a[2];
+            if (!(std::fabs(dk - dj) > eps)) return false;
+            for (int a = 0; a < 3; ++a) box.n[p][a] = n[a];
+            const int loFace = dk < dj ? k : j, hiFace = dk < dj ? j : k;
+            box.lo[p] = std::min(dk, dj);
+            box.hi[p] = std::max(dk, dj);
+            box.faces |= (uint32_t)loFace << (6 * p) | (uint32_t)hiFace << (6 * p + 3);
+        }
+        return true;
+    }
+    bool IsBoxList(int firstPrim, int count) const
+    {
+        if (count != 6 || (opt.flags & RT_UPLOAD_NO_BOXES)) return false;
+        int ids[6];
+        for (int k = 0; k < 6; ++k) ids[k] = firstPrim + k;
+        DevBox scratch;
+        return MakeDevBox(ids, scratch);
+    }
+
+    // Appends baked prims [ids] (one type) to the device arrays; returns a leaf ref.  RT_LEAF_BOX: ids are the quads
+    // of whole boxes, six each; the quads go to the quad table (hits are reported against them), one DevBox per six.
     uint32_t EmitRun(int type, const std::vector<int>& ids)
     {
+        if (type == RT_LEAF_BOX) {
+            if (ids.empty() || ids.size() % 6 != 0 || ids.size() / 6 > (size_t)RT_MAX_LEAF_PRIMS)
+                throw std::invalid_argument("box leaf size out of range");
+            const size_t firstBox = out.boxes.size();
+            for (size_t k = 0; k < ids.size(); k += 6) {
+                DevBox box;
+                if (!MakeDevBox(&ids[k], box)) throw std::invalid_argument("internal: not a box");
+                box.first_quad = (uint32_t)out.quads.size();
+                for (int f = 0; f < 6; ++f) PushQuad(baked[ids[k + f]]);
+                out.boxes.push_back(box);
+            }
+            if (out.boxes.size() > (size_t)RT_MAX_PRIMS_PER_TYPE || out.quads.size() > (size_t)RT_MAX_PRIMS_PER_TYPE)
+                throw std::invalid_argument("too many primitives");
+            return RT_REF_MAKE_LEAF(RT_LEAF_BOX, firstBox, ids.size() / 6);
+        }
         if (ids.empty() || (int)ids.size() > RT_MAX_LEAF_PRIMS) throw std::invalid_argument("leaf size out of range");
         size_t first = 0;
         if (type == RT_LEAF_SPHERE) {
@@ -677,7 +788,10 @@ struct Packer {
             }
             DevMedium dm;
             std::memset(&dm, 0, sizeof dm);
-            dm.boundary_ref = EmitRun(type, ids);
+            // a MakeBox boundary (Cornell smoke, kernel.cu:424-431): its two boundary queries are the entry and the exit
+            // of one slab test instead of two passes over six quads
+            const bool boxBoundary = type == RT_LEAF_QUAD && IsBoxList(ob.first_prim, ob.prim_count);
+            dm.boundary_ref = EmitRun(boxBoundary ? (int)RT_LEAF_BOX : type, ids);
             dm.phase_material = ob.phase_material;
             dm.neg_inv_density = -1.0 / ob.density;
             dm.medium_id = ob.medium_id;
@@ -739,6 +853,23 @@ struct Packer {
             // Instance.h:166-184) stays ONE item -- half the nodes (scene 9: 5 062 -> 2 454, the node table then fits
             // in shared memory), but every visit tests all six quads one after the other.  Measured slower than
             // one item per quad: scene 9 4.00 vs 4.19 Grays/s, scene 7 11.6 vs 13.1 (profiles/r2_ab_i.jsonl).
+            // A MakeBox list (six quads that close a box) is ONE item, tested by one slab test over its three pairs of
+            // faces (DevBox) instead of six plane + interior tests spread over several leaves.
+            if (!perObject && ob.kind == RT_OBJ_LIST && IsBoxList(ob.first_prim, ob.prim_count)) {
+                Item it;
+                it.type = RT_LEAF_BOX;
+                it.index = ob.first_prim;
+                it.first = it.count = 0;
+                it.box = Box3();
+                std::vector<int> ids;
+                for (int k = 0; k < ob.prim_count; ++k) {
+                    it.box.Grow(baked[ob.first_prim + k].box);
+                    ids.push_back(ob.first_prim + k);
+                }
+                b.items.push_back(it);
+                runOfItem.push_back(ids);
+                continue;
+            }
             bool wholeList = !perObject && ob.kind == RT_OBJ_LIST && ob.prim_count >= 2 && ob.prim_count <= opt_small_list;
             for (int k = 1; wholeList && k < ob.prim_count; ++k)
                 wholeList = baked[ob.first_prim + k].type == baked[ob.first_prim].type;
@@ -809,18 +940,19 @@ struct Packer {
             std::vector<char> take(b.items.size(), 0);
             int slots = RT_MAX_HOISTED;
             std::vector<uint32_t> refs;
-            size_t nSurface = 0, nSurfacePrims = 0;
-            bool typePresent[3] = {false, false, false};
+            size_t nSurface = 0, nSurfaceTests = 0;
+            bool typePresent[5] = {false, false, false, false, false};
             for (size_t k = 0; k < b.items.size(); ++k)
                 if (b.items[k].type != RT_LEAF_MEDIUM) {
                     ++nSurface;
-                    nSurfacePrims += runOfItem[k].size();
+                    nSurfaceTests += b.items[k].type == RT_LEAF_BOX ? 2 : runOfItem[k].size(); // a box: one slab test
                     typePresent[b.items[k].type] = true;
                 }
-            const int nTypes = (int)typePresent[0] + (int)typePresent[1] + (int)typePresent[2];
-            const bool flat = nSurface > 0 && nSurfacePrims <= (size_t)kFlatMax && nTypes <= slots;
+            int nTypes = 0;
+            for (int t : Builder::kSurfaceTypes) nTypes += (int)typePresent[t];
+            const bool flat = nSurface > 0 && nSurfaceTests <= (size_t)kFlatMax && nTypes <= slots;
             if (flat) {
-                for (int t = 0; t < 3; ++t) {
+                for (int t : Builder::kSurfaceTypes) {
                     if (!typePresent[t]) continue;
                     std::vector<int> ids;
                     for (size_t k = 0; k < b.items.size(); ++k)

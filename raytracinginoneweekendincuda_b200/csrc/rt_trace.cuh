@@ -148,7 +148,7 @@ template <> RT_DEV int32_t LdI<true>(Base<true> b, uint32_t off)
 template <> RT_DEV int32_t LdI<false>(Base<false> b, uint32_t off) { return __ldg(reinterpret_cast<const int32_t*>(b.a + off)); }
 
 template <bool SMEM> struct SceneView {
-    Base<SMEM> nodes, spheres, sphere_material, moving, quads, media, materials, mat_params;
+    Base<SMEM> nodes, spheres, sphere_material, moving, quads, boxes, media, materials, mat_params;
     // never staged: textures and their tables
     const DevTexture* textures;
     const DevPerlin* perlins;
@@ -341,6 +341,100 @@ RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, TM
     return t;
 }
 
+// One closed box (DevBox, rt_device_types.h): MakeBox's six quads (Instance.h:166-184) as they lie in the world.  The
+// reference runs Quad::Hit (Quad.h:54-99) on each of the six and keeps the closest (HittableList.h:39-57); a line
+// meets a convex box in the entry and the exit of its three slabs and nowhere else, so the closest face in [tmin, tmax]
+// is the entry face if the entry lies in the interval, else the exit face if that does.  Per pair of faces
+// t = (D - n.O)/(n.d) as in Quad.h:62, plane terms in FP64; a pair the ray runs parallel to (|n.d| < 1e-8, Quad.h:59)
+// is hit nowhere and only decides whether the line lies between its two planes.  Returns t (fp32; FinalizeHit refines
+// it against the face's own plane) or RT_MISS; `quad` = index of the face's DevQuad.
+template <bool SMEM, class TM>
+RT_DEV float HitBox(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, TM tmin, float tmax, uint32_t& quad)
+{
+    const uint32_t off = index * 128u;
+    const double2 b0 = LdD2<SMEM>(sv.boxes, off);        // n0x n0y
+    const double2 b1 = LdD2<SMEM>(sv.boxes, off + 16u);  // n0z n1x
+    const double2 b2 = LdD2<SMEM>(sv.boxes, off + 32u);  // n1y n1z
+    const double2 b3 = LdD2<SMEM>(sv.boxes, off + 48u);  // n2x n2y
+    const double2 b4 = LdD2<SMEM>(sv.boxes, off + 64u);  // n2z lo0
+    const double2 b5 = LdD2<SMEM>(sv.boxes, off + 80u);  // lo1 lo2
+    const double2 b6 = LdD2<SMEM>(sv.boxes, off + 96u);  // hi0 hi1
+    const double2 b7 = LdD2<SMEM>(sv.boxes, off + 112u); // hi2 | first_quad, faces
+    const uint32_t firstQuad = (uint32_t)__double2loint(b7.y), faces = (uint32_t)__double2hiint(b7.y);
+    const double nx[3] = {b0.x, b1.y, b3.x}, ny[3] = {b0.y, b2.x, b3.y}, nz[3] = {b1.x, b2.y, b4.x};
+    const double lo[3] = {b4.y, b5.x, b5.y}, hi[3] = {b6.x, b6.y, b7.x};
+    float tEnter = -3.402823466e+38f, tExit = 3.402823466e+38f;
+    uint32_t fEnter = 0, fExit = 0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const double den = fma(nx[p], r.d.x, fma(ny[p], r.d.y, nz[p] * r.d.z));
+        const double s = fma(nx[p], r.o.x, fma(ny[p], r.o.y, nz[p] * r.o.z));
+        if (fabs(den) < 1e-8) {
+            if (s < lo[p] || s > hi[p]) return RT_MISS;
+            continue;
+        }
+        const float inv = RcpApprox((float)den);
+        const float ta = (float)(lo[p] - s) * inv, tb = (float)(hi[p] - s) * inv;
+        const bool loFirst = ta < tb;
+        const float tn = loFirst ? ta : tb, tf = loFirst ? tb : ta;
+        const uint32_t pair = faces >> (6 * p);
+        const uint32_t fn = (loFirst ? pair : pair >> 3) & 7u, ff = (loFirst ? pair >> 3 : pair) & 7u;
+        if (tn > tEnter) {
+            tEnter = tn;
+            fEnter = fn;
+        }
+        if (tf < tExit) {
+            tExit = tf;
+            fExit = ff;
+        }
+    }
+    if (tEnter > tExit) return RT_MISS;
+    if (!((TM)tEnter < tmin) && !(tEnter > tmax)) { // closed interval, Quad.h:64
+        quad = firstQuad + fEnter;
+        return tEnter;
+    }
+    if (!((TM)tExit < tmin) && !(tExit > tmax)) {
+        quad = firstQuad + fExit;
+        return tExit;
+    }
+    return RT_MISS;
+}
+
+// The same slab test for a ConstantMedium whose boundary is a box (ConstantMedium.h:60-63): the first boundary query,
+// over (-inf, inf), returns the entry of the line into the box, the second, from t1 + 1e-4, its exit.  FP64 throughout
+// (the scatter point is the origin of the rest of the path).  False when the line misses the box.
+template <bool SMEM>
+RT_DEV bool BoxSpan(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, double& t1, double& t2)
+{
+    const uint32_t off = index * 128u;
+    const double2 b0 = LdD2<SMEM>(sv.boxes, off);
+    const double2 b1 = LdD2<SMEM>(sv.boxes, off + 16u);
+    const double2 b2 = LdD2<SMEM>(sv.boxes, off + 32u);
+    const double2 b3 = LdD2<SMEM>(sv.boxes, off + 48u);
+    const double2 b4 = LdD2<SMEM>(sv.boxes, off + 64u);
+    const double2 b5 = LdD2<SMEM>(sv.boxes, off + 80u);
+    const double2 b6 = LdD2<SMEM>(sv.boxes, off + 96u);
+    const double hi2 = LdD<SMEM>(sv.boxes, off + 112u);
+    const double nx[3] = {b0.x, b1.y, b3.x}, ny[3] = {b0.y, b2.x, b3.y}, nz[3] = {b1.x, b2.y, b4.x};
+    const double lo[3] = {b4.y, b5.x, b5.y}, hi[3] = {b6.x, b6.y, hi2};
+    t1 = -1.0e300;
+    t2 = 1.0e300;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const double den = fma(nx[p], r.d.x, fma(ny[p], r.d.y, nz[p] * r.d.z));
+        const double s = fma(nx[p], r.o.x, fma(ny[p], r.o.y, nz[p] * r.o.z));
+        if (fabs(den) < 1e-8) {
+            if (s < lo[p] || s > hi[p]) return false;
+            continue;
+        }
+        const double inv = RcpD(den);
+        const double ta = (lo[p] - s) * inv, tb = (hi[p] - s) * inv;
+        t1 = fmax(t1, fmin(ta, tb));
+        t2 = fmin(t2, fmax(ta, tb));
+    }
+    return t1 <= t2;
+}
+
 // One leaf-style run of primitives, closest hit with a shrinking tmax
 // (HittableList.h:39-57).  Returns the hit id or RT_HIT_NONE; t in tmax.
 template <int FEAT, bool SMEM, class TM>
@@ -353,6 +447,17 @@ RT_DEV uint32_t HitRun(const SceneView<SMEM>& sv, uint32_t ref, const Ray& r, do
     for (uint32_t i = 0; i < count; ++i) {
         float t;
         ++primTests;
+        // (surface queries only: a medium whose boundary is a box takes BoxSpan, never this loop -- and the
+        // feature-complete kernel is short of instruction cache, not of branches)
+        if (sizeof(TM) == sizeof(float) && (FEAT & RT_FEAT_QUAD) && type == RT_LEAF_BOX) {
+            uint32_t quad = 0;
+            t = HitBox<SMEM, TM>(sv, first + i, r, tmin, tmax, quad);
+            if (t != RT_MISS) {
+                tmax = t;
+                hit = RT_HIT_MAKE(RT_LEAF_QUAD, quad);
+            }
+            continue;
+        }
         if ((FEAT & RT_FEAT_QUAD) && type == RT_LEAF_QUAD) {
             float al, be;
             t = HitQuad<SMEM, TM>(sv, first + i, r, tmin, tmax, al, be);
@@ -557,6 +662,11 @@ RT_MEDIUM_FN bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray
         t1 = fmin(ta, tb);
         t2 = fmax(ta, tb);
         if (!(t2 > t1 + 0.0001)) return false;
+    } else if ((FEAT & RT_FEAT_QUAD) && RT_REF_TYPE(bref) == RT_LEAF_BOX && RT_REF_COUNT(bref) == 1u) {
+        // A box as the boundary (the smoke boxes of the Cornell scene, kernel.cu:424-431): entry and exit of one slab test.
+        primTests += 2;
+        if (!BoxSpan<SMEM>(sv, RT_REF_FIRST(bref), r, t1, t2)) return false;
+        if (!(t2 >= t1 + 0.0001)) return false; // second query: closed at its tMin (Quad.h:64)
     } else {
         const float big = 3.402823466e+38f;
         float t1f = big;
@@ -735,6 +845,22 @@ RT_DEV void BeginWalk(const SceneView<SMEM>& sv, const Ray& r, double a, float r
         TestLeaf<FEAT, SMEM>(sv, __ldg(&sv.hoisted[k]), r, a, rcpA, tmin, tv, seed, pixel, sample, slot, primTests);
 }
 
+// The same start with ONE copy of the leaf test in the kernel: the hoisted refs go on the traversal stack above the
+// root, the first of them into tv.ref, and the walk loop's own leaf step tests them -- still on a full warp, because
+// every lane of a round starts its walk with the same refs in the same order.  They occupy the stack only until the
+// root is popped, so the stack needs max(tree depth, n_hoisted) levels, not the sum.  For the instantiations whose
+// leaf test is large (media: two boundary queries inlined) the second copy in BeginWalk cost more in instruction
+// fetch stalls than the loop overhead it saved.
+template <bool SMEM> RT_DEV void BeginWalkStacked(const SceneView<SMEM>& sv, const Stack& stack, Trav& tv)
+{
+    tv.Begin(sv.root_ref, stack);
+    if (sv.n_hoisted > 0) {
+        TravPush(stack, tv, sv.root_ref);
+        for (int k = sv.n_hoisted - 1; k >= 1; --k) TravPush(stack, tv, __ldg(&sv.hoisted[k]));
+        tv.ref = __ldg(&sv.hoisted[0]);
+    }
+}
+
 // ----------------------------------------------------------------- textures
 // Perlin.h:38-139.  Lattice cell and fractions from the FP64 point (octave 6
 // scales it by 64, where fp32 would have lost the fraction); the rest fp32.
@@ -888,6 +1014,59 @@ RT_DEV bool BallCandidate(uint32_t bx, uint32_t by, uint32_t bz, d3& p)
 #ifndef RT_BALL_EAGER
 #define RT_BALL_EAGER 2 /* candidates pre-tested on every lane before the sequential loop: 0, 2 or 4 */
 #endif
+// RT_BALL_STRUCTURED (default): the same search written with ONE exit.  In the form above every candidate is a
+// `return` with its own copy of BallPoint behind it: the lanes of a warp leave through eight different exits and the
+// FP64 construction of the point runs once per exit that was taken, each time on the few lanes that took it (ncu, Cornell
+// smoke scene: BallPoint on 3.9 lanes, the whole function 21.6 % of the kernel's instructions on 6.5 lanes).  Here the
+// search only selects the accepted candidate's three 32-bit draws -- two candidates on every lane, then nested ifs
+// that close before the loop turns -- and the point is built once, after the warp has reconverged.  Same draws, same
+// candidate, same point.
+#ifndef RT_BALL_STRUCTURED
+#define RT_BALL_STRUCTURED 1
+#endif
+RT_DEV bool BallAccept(uint32_t bx, uint32_t by, uint32_t bz)
+{
+    const int pre = BallPreTest(bx, by, bz);
+    if (pre == 2) { // within 1e-5 of the surface (one candidate in ~1e5): decided on the exact FP64 length
+        d3 p;
+        return BallPoint(bx, by, bz, 2, p);
+    }
+    return pre == 1;
+}
+#if RT_BALL_STRUCTURED
+RT_DEV d3 RandomInUnitSphere(const StreamKey& key)
+{
+    const rt_u4 b0 = key.Block(0u);
+    rt_u4 bp = key.Block(1u); // the second block of the current group of three (four candidates)
+    const bool ok0 = BallAccept(b0.x, b0.y, b0.z), ok1 = BallAccept(b0.w, bp.x, bp.y); // both, on every lane
+    uint32_t bx = ok0 ? b0.x : b0.w, by = ok0 ? b0.y : bp.x, bz = ok0 ? b0.z : bp.y;
+    bool found = ok0 || ok1;
+    uint32_t blk = 2u;
+    while (!found) { // 23 % of the lanes; each turn: candidates 2, 3 of this group, then 0, 1 of the next
+        const rt_u4 b2 = key.Block(blk);
+        bx = bp.z, by = bp.w, bz = b2.x;
+        found = BallAccept(bx, by, bz);
+        if (!found) {
+            bx = b2.y, by = b2.z, bz = b2.w;
+            found = BallAccept(bx, by, bz);
+            if (!found) {
+                const rt_u4 c0 = key.Block(blk + 1u);
+                bx = c0.x, by = c0.y, bz = c0.z;
+                found = BallAccept(bx, by, bz);
+                if (!found) {
+                    bp = key.Block(blk + 2u);
+                    bx = c0.w, by = bp.x, bz = bp.y;
+                    found = BallAccept(bx, by, bz);
+                }
+            }
+        }
+        blk += 3u;
+    }
+    d3 p;
+    BallPoint(bx, by, bz, 1, p);
+    return p;
+}
+#else
 RT_DEV d3 RandomInUnitSphere(const StreamKey& key)
 {
     d3 p;
@@ -923,6 +1102,7 @@ RT_DEV d3 RandomInUnitSphere(const StreamKey& key)
         if (BallCandidate(b2.y, b2.z, b2.w, p)) return p;
     }
 }
+#endif
 
 RT_DEV d3 Reflect(d3 v, d3 n) { return v - (2.0 * dot(v, n)) * n; } // Vec3.h:122-125
 

@@ -21,20 +21,86 @@ def test_hoisting_policy(lib, earth):
     the r = 1000 ground sphere), every ConstantMedium (scene 9: the blue-glass medium and the r = 5000 mist whose box
     contains the whole scene, reference kernel.cu:476-482; scene 8: the two smoke boxes), and all surfaces of a tiny
     scene (scene 8: the six Cornell walls as one run of quads -- its tree is then empty)."""
-    expect = {10: [0], 0: [0], 9: [3, 3], 8: [2, 3, 3], 7: []}  # leaf-ref types: 0 sphere, 2 quad run, 3 medium
+    expect = {10: [0], 0: [0], 9: [3, 3], 8: [2, 3, 3], 7: [2, 4]}  # leaf-ref types: 0 sphere, 2 quad run, 3 medium, 4 box run
     for sid, types in expect.items():
         sc = BuiltinScene(sid, earth if sid == 9 else None)
         rc, i = pack(lib, sc.desc)
         assert rc == 0 and i.n_hoisted == len(types), (sid, i.n_hoisted)
         for k, t in enumerate(types):
-            assert (i.hoisted[k] >> 31) == 1 and ((i.hoisted[k] >> 29) & 3) == t, (sid, k, hex(i.hoisted[k]))
+            assert (i.hoisted[k] >> 31) == 1 and ((i.hoisted[k] >> 28) & 7) == t, (sid, k, hex(i.hoisted[k]))
         rc, j = pack(lib, sc.desc, flags=A.RT_UPLOAD_NO_HOIST)
         assert rc == 0 and j.n_hoisted == 0
         assert j.n_nodes >= i.n_nodes
         assert (i.n_spheres, i.n_moving, i.n_quads, i.n_media) == (j.n_spheres, j.n_moving, j.n_quads, j.n_media)
     sc = BuiltinScene(8)
     rc, i = pack(lib, sc.desc)
-    assert i.n_nodes == 2 and i.max_depth_bvh == 0 and ((i.hoisted[0] >> 19) & 1023) + 1 == 6  # empty tree, run of 6 quads
+    assert i.n_nodes == 2 and i.max_depth_bvh == 0 and ((i.hoisted[0] >> 18) & 1023) + 1 == 6  # empty tree, run of 6 quads
+
+
+def test_closed_six_quad_lists_become_slab_tested_boxes(lib, earth):
+    """rt_pack.hpp MakeDevBox: MakeBox lists (Instance.h:166-184), with or without RotateY / Translate around them,
+    are one BVH item each, tested by one slab test; their six quads stay in the quad table (hits are reported against
+    them).  Scene 7: the two Cornell boxes; scene 8: the two smoke boundaries; scene 9: the 400 ground boxes -- half
+    the nodes, and the node table then fits in shared memory.  Reference / list topologies keep the quads."""
+    for sid, boxes in ((7, 2), (8, 2), (9, 400)):
+        sc = BuiltinScene(sid, earth if sid == 9 else None)
+        rc, i = pack(lib, sc.desc)
+        rc2, j = pack(lib, sc.desc, flags=A.RT_UPLOAD_NO_BOXES)
+        assert rc == 0 and rc2 == 0 and i.n_boxes == boxes and j.n_boxes == 0, (sid, i.n_boxes, j.n_boxes)
+        assert i.n_quads == j.n_quads and i.n_nodes <= j.n_nodes
+        for bvh in (A.RT_BVH_REFERENCE, A.RT_BVH_NONE):
+            rc, k = pack(lib, sc.desc, bvh=bvh)
+            assert rc == 0 and k.n_boxes == (boxes if sid == 8 else 0)  # (a medium's boundary is not a BVH item)
+    sc = BuiltinScene(9, earth)
+    rc, i = pack(lib, sc.desc)
+    assert i.n_nodes * 32 < 100 * 1024
+
+
+def _six_quad_scene(shift_top=0.0, tilt=0.0):
+    """One owning list of six quads laid out like MakeBox((0,0,0),(1,2,3)) (Instance.h:166-184) plus a sphere."""
+    lo, hi = (0.0, 0.0, 0.0), (1.0, 2.0, 3.0)
+    dx, dy, dz = (1.0, 0.0, 0.0), (0.0, 2.0, 0.0), (0.0, 0.0, 3.0)
+
+    def neg(v):
+        return tuple(-c for c in v)
+
+    quads = [((lo[0], lo[1], hi[2]), dx, dy), ((hi[0], lo[1], hi[2]), neg(dz), dy), ((hi[0], lo[1], lo[2]), neg(dx), dy),
+             ((lo[0], lo[1], lo[2]), dz, dy), ((lo[0], hi[1] + shift_top, hi[2]), dx, (0.0, tilt, -3.0)),
+             ((lo[0], lo[1], lo[2]), dx, dz)]
+    prims = (A.rt_prim * 7)()
+    for k, (q, u, v) in enumerate(quads):
+        prims[k].type = A.RT_PRIM_QUAD
+        prims[k].a[:] = list(q)
+        prims[k].b[:] = list(u)
+        prims[k].c[:] = list(v)
+    prims[6].type = A.RT_PRIM_SPHERE
+    prims[6].a[:] = [5.0, 5.0, 5.0]
+    prims[6].radius = 1.0
+    objs = (A.rt_object * 2)()
+    objs[0].kind = A.RT_OBJ_LIST
+    objs[0].first_prim, objs[0].prim_count = 0, 6
+    objs[0].bbox[:] = [0, 1, 0, 2.5, 0, 3]
+    objs[1].kind = A.RT_OBJ_PRIM
+    objs[1].first_prim, objs[1].prim_count = 6, 1
+    objs[1].bbox[:] = [4, 6, 4, 6, 4, 6]
+    mats = (A.rt_material * 1)()
+    mats[0].type = A.RT_MAT_LAMBERTIAN
+    mats[0].texture = 0
+    tex = (A.rt_texture * 1)()
+    tex[0].type = A.RT_TEX_SOLID
+    d = A.rt_scene_desc(abi_version=A.RT_ABI_VERSION, n_objects=2, n_prims=7, n_materials=1, n_textures=1,
+                        objects=objs, prims=prims, materials=mats, textures=tex)
+    d._keep = (prims, objs, mats, tex)
+    return d
+
+
+def test_an_open_or_skewed_six_quad_list_is_not_a_box(lib):
+    """Six quads that do not close a box (one face lifted off; one face tilted) stay six quads."""
+    for kw, want in ((dict(), 1), (dict(shift_top=0.25), 0), (dict(tilt=0.1), 0)):
+        d = _six_quad_scene(**kw)
+        rc, i = pack(lib, C.byref(d))
+        assert rc == 0, lib.rt_last_error()
+        assert i.n_boxes == want and i.n_quads == 6, (kw, i.n_boxes)
 
 
 def test_reference_and_list_modes_never_hoist(lib):

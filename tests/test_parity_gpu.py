@@ -122,6 +122,24 @@ def test_hoisting_does_not_change_the_image(earth, sid):
     assert (a == b).all(axis=2).mean() >= 0.9995
 
 
+@pytest.mark.parametrize("sid,W,H,spp", [(7, 128, 128, 4), (8, 128, 128, 4), (9, 160, 90, 3)])
+def test_slab_tested_boxes_do_not_change_the_image(earth, sid, W, H, spp):
+    """MakeBox lists (Instance.h:166-184: the two Cornell boxes, the smoke boxes' boundaries, scene 9's 400 ground
+    boxes) are tested as ONE slab test over their three pairs of faces (DevBox, rt_trace.cuh HitBox / BoxSpan) and
+    their hits reported against the face's own quad: same closest face as the reference's six Quad::Hit calls, so the
+    same image as with RT_UPLOAD_NO_BOXES, which tests the quads one by one."""
+    sc = scene_for(sid, earth)
+    cam = sc.camera(W, H, spp, 50)
+    a, sa, _ = gpu_render(sc, cam)
+    b, sb, _ = gpu_render(sc, cam, upload_flags=A.RT_UPLOAD_NO_BOXES)
+    i = A.rt_pack_info()
+    o = A.rt_upload_options(flags=0)
+    assert sc.lib.rt_scene_pack_info(sc.desc, C.byref(o), C.byref(i)) == 0 and i.n_boxes >= 2
+    assert abs(int(sa.rays) - int(sb.rays)) <= 1e-4 * sb.rays
+    ok = (np.abs(a - b) <= REL_TOL * np.abs(b) + ABS_FLOOR).all(axis=2)
+    assert ok.mean() >= 0.9995, f"scene {sid}: {ok.mean() * 100:.3f}% of pixels within 1e-3 of the quad-by-quad render"
+
+
 @pytest.mark.parametrize("sid,W,H,spp", [(10, 200, 113, 6), (0, 96, 54, 4), (7, 64, 64, 6), (8, 64, 64, 6), (9, 96, 54, 3)])
 def test_wavefront_variant_renders_the_same_image_as_the_megakernel(earth, sid, W, H, spp):
     """Same per-pixel sample order and the same device functions: the on-chip wavefront
