@@ -283,9 +283,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ GPU arm
 OTHER_CONFIGS = [  # BASELINE.json configs[2..4] at their image sizes, spp bounded so the whole bench stays within minutes
-    {"name": "configs[2] bouncing spheres (motion blur + checker)", "scene": 0, "width": 1920, "height": 1080, "spp": 64, "of": 512},
-    {"name": "configs[3] Cornell smoke (quads, instances, media)", "scene": 8, "width": 1024, "height": 1024, "spp": 64, "of": 4096},
-    {"name": "configs[4] Book 2 final", "scene": 9, "width": 3840, "height": 2160, "spp": 8, "of": 10000},
+    {"name": "configs[2] bouncing spheres (motion blur + checker)", "scene": 0, "width": 1920, "height": 1080, "spp": 256, "of": 512},
+    {"name": "configs[3] Cornell smoke (quads, instances, media)", "scene": 8, "width": 1024, "height": 1024, "spp": 256, "of": 4096},
+    {"name": "configs[4] Book 2 final", "scene": 9, "width": 3840, "height": 2160, "spp": 32, "of": 10000},
 ]
 
 
