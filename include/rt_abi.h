@@ -223,7 +223,13 @@ typedef struct rt_render_params {
 enum {
     RT_FLAG_STATS = 0x100,          /* instrumented kernel: fills rt_stats.paths/node_tests/prim_tests */
     RT_FLAG_SCENE_IN_GLOBAL = 0x200, /* do not stage the scene in shared memory (A/B test)              */
-    RT_FLAG_NODES_IN_GLOBAL = 0x400  /* a scene too large to stage: do not stage its node table either  */
+    RT_FLAG_NODES_IN_GLOBAL = 0x400, /* a scene too large to stage: do not stage its node table either  */
+    RT_FLAG_IMPORTANCE = 0x800       /* importance sampling of the lights (phase 4 of the reference's roadmap, README.md:37-42,
+                                        not implemented there): every Lambertian / Isotropic bounce draws its direction
+                                        from 1/2 (the reference's own scattering density) + 1/2 (density of the directions
+                                        towards the quads and spheres that carry a DiffuseLight material) and is weighed
+                                        with scattering density / mixture density -- the same image in expectation as
+                                        without the flag, with less noise where lights are small.  Hit-queue kernel only. */
     /* bits 4-5 and 12-30 are development tuning knobs of the kernels (csrc/rt_device.cu)             */
 };
 
@@ -313,7 +319,7 @@ typedef struct rt_pack_info {
     uint32_t hoisted[4];   /* their leaf refs: type in bits 30..28 (0 sphere, 1 moving, 2 quad, 3 medium, 4 box) */
     uint64_t staged_bytes; /* nodes + primitives + materials: what a CTA stages in shared memory when it fits */
     int32_t n_boxes;       /* closed six-quad boxes tested by one slab test (their quads are counted in n_quads) */
-    int32_t _pad;
+    int32_t n_lights;      /* quads / spheres with a DiffuseLight material: the sampling targets of RT_FLAG_IMPORTANCE */
 } rt_pack_info;
 int rt_scene_pack_info(const rt_scene_desc* scene, const rt_upload_options* opt, rt_pack_info* out);
 

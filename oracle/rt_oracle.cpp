@@ -39,6 +39,8 @@
 
 namespace {
 
+const double kPiValue = 3.1415926535897932385;
+
 // ----------------------------------------------------------------- counters
 struct Stats {
     uint64_t rays = 0, paths = 0, box_tests = 0, sphere_tests = 0, quad_tests = 0, medium_tests = 0, draws = 0;
@@ -108,6 +110,13 @@ struct Stream {
     {
         if (stats) ++stats->draws;
         return At(seed, pixel, sample, slot, 1u + 2u * id + visit, 0);
+    }
+    // Importance sampling: draw `dim` (0 strategy, 1 light index, 2, 3 the point on the light) of the bounce's own
+    // keyed domain, so that the sequential scatter draws of domain 0 keep their positions.
+    float Importance(uint32_t d) const
+    {
+        if (stats) ++stats->draws;
+        return At(seed, pixel, sample, slot, 32u, d);
     }
 };
 
@@ -217,6 +226,10 @@ template <class R> struct Scene {
     std::vector<Box<R>> node_box;
     int root = -1;
     std::vector<int> medium_visits;
+    // Importance sampling (the reference's roadmap, README.md:37-42, unimplemented there): the sampling
+    // targets are the quads and spheres with a DiffuseLight material, in primitive order (media boundaries excluded).
+    bool importance = false;
+    std::vector<int> lights;
 };
 
 // BvhNode.h:50-90 + DeviceSort/BoxCompare :170-193, on object indices.
@@ -328,6 +341,17 @@ template <class R> bool LoadScene(const rt_scene_desc* d, Scene<R>& s)
     s.nodes.clear();
     s.node_box.clear();
     s.root = BuildReferenceBvh(s, order, 0, d->n_objects, bbox);
+    s.lights.clear();
+    for (int o = 0; o < d->n_objects; ++o) {
+        if (d->objects[o].kind == RT_OBJ_MEDIUM) continue;
+        for (int k = 0; k < d->objects[o].prim_count; ++k) {
+            const int i = d->objects[o].first_prim + k;
+            const rt_prim& p = d->prims[i];
+            if ((p.type == RT_PRIM_QUAD || p.type == RT_PRIM_SPHERE) && d->materials[p.material].type == RT_MAT_DIFFUSE_LIGHT)
+                s.lights.push_back(i);
+        }
+    }
+    std::sort(s.lights.begin(), s.lights.end());
     // trap T2: how often the reference topology references each medium leaf
     s.medium_visits.assign(n_media, 0);
     for (const BvhNodeRef& n : s.nodes) {
@@ -688,12 +712,122 @@ template <class R> bool NearZero(const V3<R>& v)
     return std::fabs(v[0]) < th && std::fabs(v[1]) < th && std::fabs(v[2]) < th;
 }
 
+// ------------------------------------------------- importance sampling (f4)
+// The machinery of "Ray Tracing: The Rest of Your Life" (P. Shirley et al., v4.0.1, the book the reference's roadmap
+// names for its phase 4: PDFs, mixture density, sampling of lights, orthonormal basis) applied to the scattering the
+// reference HAS: its Lambertian sends the ray to N + (point in the unit ball) (Material.h:68-86), whose direction
+// density is 2 cos^3(theta) / pi (chord of the ball along the direction, cubed, over the ball's volume), and weighs
+// it with the albedo alone -- i.e. the scattering function is albedo * 2 cos^3 / pi.  Sampling the mixture
+//   1/2 * (that density) + 1/2 * (density of the directions towards the lights)
+// and weighing with (scattering density) / (mixture density) estimates the SAME image with less noise wherever
+// lights are small.  Isotropic (Material.h:151-162) is uniform on the sphere: 1 / 4 pi.
+
+// Object -> world for a point / a vector of primitive p (Instance.h:136-147 the other way round).
+template <class R> V3<R> ToWorld(const Scene<R>& s, const Prim<R>& p, V3<R> v, bool isPoint)
+{
+    for (int k = p.xform_count - 1; k >= 0; --k) {
+        const Xform<R>& x = s.xforms[p.first_xform + k];
+        if (x.type == RT_XFORM_TRANSLATE) {
+            if (isPoint) v = v + x.offset;
+        } else {
+            v = V3<R>(x.cos_t * v[0] + x.sin_t * v[2], v[1], -x.sin_t * v[0] + x.cos_t * v[2]);
+        }
+    }
+    return v;
+}
+
+// Book 3, quad::pdf_value / sphere::pdf_value: density (per solid angle, seen from `o`) with which light.Random
+// produces direction `d`; 0 when the ray (o, d) misses the light.
+template <class R> R LightPdf(const Scene<R>& s, int prim, const V3<R>& o, const V3<R>& d, Stats& st)
+{
+    const Prim<R>& p = s.prims[prim];
+    Ray<R> r;
+    r.o = o;
+    r.d = d;
+    HitRec<R> rec;
+    if (!HitPrim(s, p, r, R(0.001), Limits<R>::Max(), rec, st)) return R(0);
+    if (p.type == RT_PRIM_QUAD) {
+        const R area = Cross(p.b, p.c).Length();
+        const R dist2 = rec.t * rec.t * d.LengthSquared();
+        const R cosine = std::fabs(Dot(d, rec.n) / d.Length());
+        return dist2 / (cosine * area);
+    }
+    const V3<R> c = ToWorld(s, p, p.a, true);
+    const R cosMax = std::sqrt(R(1) - p.radius * p.radius / (c - o).LengthSquared());
+    return R(1) / (R(2) * (R)kPiValue * (R(1) - cosMax));
+}
+
+// Book 3, quad::random / sphere::random (onb + random_to_sphere): a direction from `o` towards the light.
+template <class R> V3<R> LightDirection(const Scene<R>& s, int prim, const V3<R>& o, R r1, R r2)
+{
+    const Prim<R>& p = s.prims[prim];
+    if (p.type == RT_PRIM_QUAD) return ToWorld(s, p, p.a + r1 * p.b + r2 * p.c, true) - o;
+    const V3<R> dir = ToWorld(s, p, p.a, true) - o;
+    const R dist2 = dir.LengthSquared();
+    // onb: w = unit(dir), a = |w.x| > 0.9 ? y : x, v = unit(w x a), u = w x v
+    const V3<R> w = Unit(dir);
+    const V3<R> a = std::fabs(w[0]) > R(0.9) ? V3<R>(0, 1, 0) : V3<R>(1, 0, 0);
+    const V3<R> v = Unit(Cross(w, a));
+    const V3<R> u = Cross(w, v);
+    const R z = R(1) + r2 * (std::sqrt(R(1) - p.radius * p.radius / dist2) - R(1));
+    const R phi = R(2) * (R)kPiValue * r1;
+    const R rad = std::sqrt(R(1) - z * z);
+    return (std::cos(phi) * rad) * u + (std::sin(phi) * rad) * v + z * w;
+}
+
+// The scattered direction and the weight (scattering density / mixture density) of a Lambertian or Isotropic hit.
+// Returns false when the weight is 0 (the direction carries nothing).
 template <class R>
-bool Scatter(const Scene<R>& s, const Ray<R>& in, const HitRec<R>& rec, V3<R>& atten, Ray<R>& out, Stream& rng)
+bool ScatterImportance(const Scene<R>& s, bool lambertian, const HitRec<R>& rec, V3<R>& dir, R& weight, Stream& rng, Stats& st)
+{
+    const int nLights = (int)s.lights.size();
+    const R u0 = (R)rng.Importance(0);
+    if (nLights > 0 && u0 < R(0.5)) {
+        int k = (int)((R)rng.Importance(1) * (R)nLights);
+        if (k > nLights - 1) k = nLights - 1;
+        const R r1 = (R)rng.Importance(2), r2 = (R)rng.Importance(3);
+        dir = LightDirection(s, s.lights[(size_t)k], rec.p, r1, r2);
+    } else {
+        const V3<R> ball = RandomInUnitSphere<R>(rng);
+        if (lambertian) {
+            dir = rec.n + ball;
+            if (NearZero(dir)) dir = rec.n;
+        } else {
+            dir = Unit(ball);
+        }
+    }
+    const R len = dir.Length();
+    if (!(len > R(0))) return false;
+    R pMat;
+    if (lambertian) {
+        const R c = Dot(dir, rec.n) / len;
+        pMat = c > R(0) ? R(2) * c * c * c / (R)kPiValue : R(0);
+    } else {
+        pMat = R(1) / (R(4) * (R)kPiValue);
+    }
+    R pdf = pMat;
+    if (nLights > 0) {
+        R pLight = 0;
+        for (int k = 0; k < nLights; ++k) pLight = pLight + LightPdf(s, s.lights[(size_t)k], rec.p, dir, st);
+        pdf = R(0.5) * (pLight / (R)nLights) + R(0.5) * pMat;
+    }
+    if (!(pMat > R(0)) || !(pdf > R(0))) return false;
+    weight = pMat / pdf;
+    return true;
+}
+
+template <class R>
+bool Scatter(const Scene<R>& s, const Ray<R>& in, const HitRec<R>& rec, V3<R>& atten, Ray<R>& out, Stream& rng, Stats& st)
 {
     const rt_material& m = s.materials[rec.material];
     out.time = in.time;
     out.o = rec.p;
+    if (s.importance && (m.type == RT_MAT_LAMBERTIAN || m.type == RT_MAT_ISOTROPIC)) {
+        R weight = 0;
+        if (!ScatterImportance(s, m.type == RT_MAT_LAMBERTIAN, rec, out.d, weight, rng, st)) return false;
+        atten = weight * TextureValue(s, m.texture, rec.u, rec.v, rec.p);
+        return true;
+    }
     switch (m.type) {
     case RT_MAT_LAMBERTIAN: { // Material.h:68-86
         V3<R> dir = rec.n + RandomInUnitSphere<R>(rng);
@@ -812,7 +946,7 @@ V3<R> RayColor(const Scene<R>& s, const Cam<R>& cam, Ray<R> ray, Stream& rng, bo
         }
         Ray<R> scattered;
         V3<R> atten;
-        if (!Scatter(s, ray, rec, atten, scattered, rng)) return accumulated;
+        if (!Scatter(s, ray, rec, atten, scattered, rng, st)) return accumulated;
         throughput = throughput * atten;
         ray = scattered;
     }
@@ -861,11 +995,13 @@ void RenderRows(const Scene<R>& s, const Cam<R>& cam, const Window& win, int j0,
 }
 
 template <class R>
-int RenderT(const rt_scene_desc* d, const rt_camera* c, const Window* window, int s0, int s1, uint32_t seed, bool useBvh,
+int RenderT(const rt_scene_desc* d, const rt_camera* c, const Window* window, int s0, int s1, uint32_t seed, int mode,
             int nThreads, double* out, Stats& total)
 {
+    const bool useBvh = (mode & 1) != 0;
     Scene<R> s;
     if (!LoadScene(d, s)) return -1;
+    s.importance = (mode & 2) != 0;
     const Cam<R> cam(*c);
     if (nThreads < 1) nThreads = 1;
     std::vector<Stats> st((size_t)nThreads);
@@ -900,7 +1036,8 @@ struct oracle_stats {
 };
 
 // out: W*H*3 doubles, row 0 = bottom row, linear radiance SUM over [s0,s1).
-// bvh: 1 = reference-topology BVH (BvhNode.h), 0 = linear list.
+// bvh: bit 0: 1 = reference-topology BVH (BvhNode.h), 0 = linear list; bit 1 (value 2): importance sampling of the
+// lights (ScatterImportance above; the default, 0, is the reference's scattering).
 // precision: 64 = the oracle; 32 = float study build of the same code.
 static int OracleRender(const rt_scene_desc* scene, const rt_camera* cam, const Window* win, int sample_begin,
                         int sample_end, uint32_t seed, int bvh, int precision, int n_threads, double* out,
@@ -931,9 +1068,9 @@ static int OracleRender(const rt_scene_desc* scene, const rt_camera* cam, const 
     Stats st;
     int rc;
     if (precision == 32)
-        rc = RenderT<float>(scene, cam, win, sample_begin, sample_end, seed, bvh != 0, n_threads, out, st);
+        rc = RenderT<float>(scene, cam, win, sample_begin, sample_end, seed, bvh, n_threads, out, st);
     else
-        rc = RenderT<double>(scene, cam, win, sample_begin, sample_end, seed, bvh != 0, n_threads, out, st);
+        rc = RenderT<double>(scene, cam, win, sample_begin, sample_end, seed, bvh, n_threads, out, st);
     if (rc != 0) return rc;
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
@@ -1015,7 +1152,7 @@ int oracle_trace_path(const rt_scene_desc* scene, const rt_camera* cam, int i, i
         o[7] = s.materials[rec.material].type;
         Ray<double> scattered;
         V3<double> atten;
-        if (!Scatter(s, ray, rec, atten, scattered, rng)) break;
+        if (!Scatter(s, ray, rec, atten, scattered, rng, st)) break;
         ray = scattered;
     }
     return n;

@@ -26,6 +26,7 @@ RT_BVH_SAH, RT_BVH_REFERENCE, RT_BVH_NONE = 0, 1, 2
 RT_FLAG_STATS = 0x100
 RT_FLAG_SCENE_IN_GLOBAL = 0x200
 RT_FLAG_NODES_IN_GLOBAL = 0x400
+RT_FLAG_IMPORTANCE = 0x800
 RT_UPLOAD_NO_HOIST = 1
 RT_UPLOAD_REDUCE_NCCL = 2
 RT_UPLOAD_WHOLE_LISTS = 4
@@ -124,7 +125,7 @@ class rt_pack_info(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_spheres", C.c_int32), ("n_moving", C.c_int32), ("n_quads", C.c_int32),
                 ("n_media", C.c_int32), ("n_materials", C.c_int32), ("n_mat_params", C.c_int32),
                 ("max_depth_bvh", C.c_int32), ("features", C.c_int32), ("n_hoisted", C.c_int32),
-                ("hoisted", C.c_uint32 * 4), ("staged_bytes", C.c_uint64), ("n_boxes", C.c_int32), ("_pad", C.c_int32)]
+                ("hoisted", C.c_uint32 * 4), ("staged_bytes", C.c_uint64), ("n_boxes", C.c_int32), ("n_lights", C.c_int32)]
 
 
 def declare_host(lib: C.CDLL) -> None:

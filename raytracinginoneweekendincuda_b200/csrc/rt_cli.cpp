@@ -6,10 +6,11 @@
 //
 //   rt_cli --scene 10 --width 1200 --height 675 --spp 10 --depth 50 --out out.ppm
 //          [--seed 1984] [--device 0 | --gpus N] [--earth earthmap.jpg] [--bvh sah|reference|list]
-//          [--variant auto|hitqueue|headtail|megakernel|wavefront] [--p6] [--progressive BATCH] [--nccl]
+//          [--variant auto|hitqueue|headtail|megakernel|wavefront] [--p6] [--progressive BATCH] [--nccl] [--importance]
 //   --gpus N         one process, N devices: samples split across them, accumulators reduced on device 0
 //   --earth FILE     the image texture of scenes 2 and 9: a baseline JPEG, decoded by the library as RtwImage does
 //   --progressive B  re-write the output file after every B samples while the next batch renders
+//   --importance     RT_FLAG_IMPORTANCE: diffuse bounces sample the lights (same image in expectation, less noise)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -47,7 +48,7 @@ static void OnFrame(void* user, const float*, const uint8_t* srgb8, int32_t done
 int main(int argc, char** argv)
 {
     int sceneId = 9, width = 1440, height = 720, spp = -1, depth = 50, device = 0, bvh = RT_BVH_SAH, gpus = 1;
-    int progressive = 0, uploadFlags = 0;
+    int progressive = 0, uploadFlags = 0, renderFlags = 0;
     unsigned seed = 1984;
     bool binary = false;
     int variant = RT_VARIANT_AUTO;
@@ -73,6 +74,7 @@ int main(int argc, char** argv)
         else if (a == "--earth") earthPath = next("--earth");
         else if (a == "--progressive") progressive = std::atoi(next("--progressive"));
         else if (a == "--nccl") uploadFlags |= RT_UPLOAD_REDUCE_NCCL;
+        else if (a == "--importance") renderFlags |= RT_FLAG_IMPORTANCE;
         else if (a == "--p6") binary = true;
         else if (a == "--variant") {
             const std::string v = next("--variant");
@@ -141,6 +143,7 @@ int main(int argc, char** argv)
     p.seed = seed;
     p.clear = 1;
     p.variant = variant;
+    p.flags = renderFlags;
     const auto t0 = std::chrono::steady_clock::now();
     if (progressive > 0) {
         Progress pr{out, width, height, binary, t0};

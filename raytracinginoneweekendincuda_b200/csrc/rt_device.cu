@@ -180,14 +180,23 @@ constexpr int kFeatAll = RT_FEAT_MOVING | RT_FEAT_QUAD | RT_FEAT_MEDIUM | RT_FEA
 // and moving-sphere code it is half the size of the feature-complete one.
 constexpr int kFeatBox = RT_FEAT_QUAD | RT_FEAT_MEDIUM;
 
-KernelFn PickHitQueueBox(bool smem, bool stats)
+template <int FEAT> KernelFn PickHitQueue(bool smem, bool stats)
 {
-    if (smem) return stats ? RenderHitQueue<kFeatBox, true, true> : RenderHitQueue<kFeatBox, true, false>;
-    return stats ? RenderHitQueue<kFeatBox, false, true> : RenderHitQueue<kFeatBox, false, false>;
+    if (smem) return stats ? RenderHitQueue<FEAT, true, true> : RenderHitQueue<FEAT, true, false>;
+    return stats ? RenderHitQueue<FEAT, false, true> : RenderHitQueue<FEAT, false, false>;
 }
+KernelFn PickHitQueueBox(bool smem, bool stats) { return PickHitQueue<kFeatBox>(smem, stats); }
 
-KernelFn PickKernelForFeatures(int features, int variant, bool smem, bool stats, int* picked)
+// RT_FLAG_IMPORTANCE: two more classes of the hit-queue kernel, with the light-sampling code in their Scatter.
+constexpr int kFeatBoxImportance = kFeatBox | RT_FEAT_IMPORTANCE, kFeatAllImportance = kFeatAll | RT_FEAT_IMPORTANCE;
+
+KernelFn PickKernelForFeatures(int features, int variant, bool smem, bool stats, int* picked, bool importance = false)
 {
+    if (importance) {
+        const bool boxClass = (features & ~kFeatBox) == 0;
+        *picked = boxClass ? kFeatBoxImportance : kFeatAllImportance;
+        return boxClass ? PickHitQueue<kFeatBoxImportance>(smem, stats) : PickHitQueue<kFeatAllImportance>(smem, stats);
+    }
     if (features == 0) {
         *picked = kFeatSpheres;
         return PickKernel<kFeatSpheres>(variant, smem, stats);
@@ -547,8 +556,17 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
     RT_CUDA(cudaMemsetAsync(d.tileCounter, 0, sizeof(unsigned int), stream));
 
     int variant = p->variant;
+    const bool importance = (p->flags & RT_FLAG_IMPORTANCE) != 0;
     if (variant == RT_VARIANT_AUTO)
-        variant = (long long)end - begin <= RT_HT_MAX_SAMPLES ? RT_VARIANT_HITQUEUE : RT_VARIANT_MEGAKERNEL;
+        variant = ((long long)end - begin <= RT_HT_MAX_SAMPLES || importance) ? RT_VARIANT_HITQUEUE : RT_VARIANT_MEGAKERNEL;
+    if (importance && variant != RT_VARIANT_HITQUEUE) {
+        rt_set_error("rt_render: RT_FLAG_IMPORTANCE is implemented by the hit-queue kernel (RT_VARIANT_AUTO / _HITQUEUE)");
+        return RT_ERR_UNSUPPORTED;
+    }
+    if (importance && (long long)end - begin > RT_HT_MAX_SAMPLES) {
+        rt_set_error("rt_render: RT_FLAG_IMPORTANCE takes at most %d samples per device and call", RT_HT_MAX_SAMPLES);
+        return RT_ERR_INVALID;
+    }
     const bool wave = variant == RT_VARIANT_WAVEFRONT;
     const bool hitQueue = variant == RT_VARIANT_HITQUEUE;
     const bool queued = variant == RT_VARIANT_HEADTAIL || hitQueue; // the two queue kernels share their launch shape
@@ -590,6 +608,7 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
 
     int featClass = d.dev.features == 0 ? kFeatSpheres : ((d.dev.features & ~kFeatMotion) == 0 ? kFeatMotion : kFeatAll);
     if (hitQueue && featClass == kFeatAll && (d.dev.features & ~kFeatBox) == 0) featClass = kFeatBox;
+    if (importance) featClass = (d.dev.features & ~kFeatBox) == 0 ? kFeatBoxImportance : kFeatAllImportance;
     const int maxThreads = wave ? 512 : (queued ? HtMaxThreads(featClass) : MegaMaxThreads(featClass));
     int threads = p->block_threads > 0 ? p->block_threads : maxThreads;
     threads = std::max(32, std::min(maxThreads, (threads / 32) * 32));
@@ -643,7 +662,7 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
         rt_set_error("rt_render: block of %d threads needs %zu B of shared memory (max %d)", threads, smemBytes, d.maxSmemOptin);
         return RT_ERR_INVALID;
     }
-    KernelFn fn = PickKernelForFeatures(d.dev.features, variant, smem, wantStats, &h->pickedFeatures);
+    KernelFn fn = PickKernelForFeatures(d.dev.features, variant, smem, wantStats, &h->pickedFeatures, importance);
     h->pickedVariant = variant;
     h->pickedThreads = threads;
     RT_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
@@ -727,6 +746,7 @@ int rt_scene_pack_info(const rt_scene_desc* scene, const rt_upload_options* opt,
         out->n_moving = (int32_t)p.moving.size();
         out->n_quads = (int32_t)p.quads.size();
         out->n_boxes = (int32_t)p.boxes.size();
+        out->n_lights = (int32_t)p.lights.size();
         out->n_media = (int32_t)p.media.size();
         out->n_materials = (int32_t)p.materials.size();
         out->n_mat_params = (int32_t)p.mat_params.size();
@@ -803,6 +823,7 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
     const size_t oMatParams = ab.Add(packed->mat_params);
     const size_t oTextures = ab.Add(packed->textures), oPerlins = ab.Add(packed->perlins);
     const size_t oUvFrames = ab.Add(packed->uv_frames);
+    const size_t oLights = ab.Add(packed->lights);
     const size_t oHoisted = ab.Add(std::vector<uint32_t>(packed->hoisted, packed->hoisted + RT_MAX_HOISTED));
     std::vector<DevImage> images(std::max<size_t>(1, packed->image_bytes.size()));
     std::memset(images.data(), 0, images.size() * sizeof(DevImage));
@@ -858,6 +879,8 @@ int rt_scene_upload(const rt_scene_desc* scene, const rt_upload_options* opt, rt
         d.dev.perlins = reinterpret_cast<const DevPerlin*>(d.arena + oPerlins);
         d.dev.images = reinterpret_cast<const DevImage*>(d.arena + oImages);
         d.dev.uv_frames = reinterpret_cast<const DevUvFrame*>(d.arena + oUvFrames);
+        d.dev.lights = reinterpret_cast<const DevLight*>(d.arena + oLights);
+        d.dev.n_lights = (int)packed->lights.size();
         d.dev.arena = reinterpret_cast<const uint8_t*>(d.arena);
         d.stats = reinterpret_cast<unsigned long long*>(d.arena + oStats);
         d.tileCounter = reinterpret_cast<unsigned int*>(d.arena + oTile);

@@ -113,6 +113,17 @@ struct RT_ALIGN(16) DevMedium {
     double _p;
 };
 
+// ---- Light: a sampling target of the importance-sampling mode (RT_FLAG_IMPORTANCE): a quad or a sphere
+// whose material is a DiffuseLight.  96 bytes, FP64, read once per diffuse bounce.
+struct RT_ALIGN(16) DevLight {
+    double a[3]; // quad: Q | sphere: centre
+    double b[3]; // quad: u | sphere: radius, 0, 0
+    double c[3]; // quad: v
+    uint32_t hit; // RT_HIT_MAKE(type, index) of the primitive in its device table
+    uint32_t _p;
+    double area;  // quad: |u x v|
+};
+
 // ---- Material: 16 bytes = one 128-bit load.  Book 1 has one material per sphere (486 of them), and the table is
 // staged in shared memory next to the BVH: at 32 bytes it was a quarter of the staged scene.  The FP64 parameter of
 // the two materials that have one (metal fuzz, dielectric index: they enter the scattered direction, which is FP64
@@ -172,6 +183,7 @@ struct RT_ALIGN(16) DevImage {
 #define RT_FEAT_MEDIUM 4
 #define RT_FEAT_TEXTURE 8        /* any non-solid texture */
 #define RT_FEAT_TEXTURE_HEAVY 16 /* image or Perlin-noise textures (their code costs ~25 registers) */
+#define RT_FEAT_IMPORTANCE 32    /* not a scene property: the kernel class RT_FLAG_IMPORTANCE renders with */
 
 struct DevScene {
     const DevNode* nodes;
@@ -187,11 +199,12 @@ struct DevScene {
     const DevPerlin* perlins;
     const DevImage* images;
     const DevUvFrame* uv_frames;
+    const DevLight* lights; // sampling targets of RT_FLAG_IMPORTANCE
     const uint8_t* arena; // base of the scene arena (image texel offsets are relative to it)
     uint32_t root_ref;
     const uint32_t* hoisted; // RT_MAX_HOISTED leaf refs in the arena, tested before the tree is entered
     int32_t n_hoisted;
-    int32_t n_nodes, n_spheres, n_moving, n_quads, n_boxes, n_media, n_materials, n_textures;
+    int32_t n_nodes, n_spheres, n_moving, n_quads, n_boxes, n_media, n_materials, n_textures, n_lights;
     int32_t features;
 };
 

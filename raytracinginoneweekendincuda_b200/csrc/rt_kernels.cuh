@@ -102,6 +102,8 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
     sv.perlins = scene.perlins;
     sv.images = scene.images;
     sv.uv_frames = scene.uv_frames;
+    sv.lights = scene.lights;
+    sv.n_lights = scene.n_lights;
     sv.arena = scene.arena;
     sv.root_ref = scene.root_ref;
     sv.nodes_shared = false;

@@ -87,6 +87,7 @@ struct Packed {
     std::vector<DevMaterial> materials;
     std::vector<double> mat_params;
     std::vector<DevUvFrame> uv_frames;
+    std::vector<DevLight> lights; // quads / spheres with a DiffuseLight material, in primitive order
     std::vector<DevTexture> textures;
     std::vector<DevPerlin> perlins;
     std::vector<std::vector<uint8_t>> image_bytes;
@@ -439,6 +440,7 @@ struct Packer {
     Packed out;
     std::vector<Baked> baked;         // surfaces first, then medium boundaries
     std::vector<int> bakedOfPrim;     // desc prim index -> baked index
+    std::vector<uint32_t> hitOfBaked; // baked index -> RT_HIT_MAKE(type, device index), filled as the runs are emitted
 
     Packer(const rt_scene_desc& desc, const rt_upload_options& o) : d(desc), opt(o) {}
 
@@ -625,7 +627,10 @@ struct Packer {
                 DevBox box;
                 if (!MakeDevBox(&ids[k], box)) throw std::invalid_argument("internal: not a box");
                 box.first_quad = (uint32_t)out.quads.size();
-                for (int f = 0; f < 6; ++f) PushQuad(baked[ids[k + f]]);
+                for (int f = 0; f < 6; ++f) {
+                    hitOfBaked[ids[k + f]] = RT_HIT_MAKE(RT_LEAF_QUAD, out.quads.size());
+                    PushQuad(baked[ids[k + f]]);
+                }
                 out.boxes.push_back(box);
             }
             if (out.boxes.size() > (size_t)RT_MAX_PRIMS_PER_TYPE || out.quads.size() > (size_t)RT_MAX_PRIMS_PER_TYPE)
@@ -636,13 +641,19 @@ struct Packer {
         size_t first = 0;
         if (type == RT_LEAF_SPHERE) {
             first = out.spheres.size();
-            for (int i : ids) PushSphere(baked[i]);
+            for (int i : ids) {
+                hitOfBaked[i] = RT_HIT_MAKE(RT_LEAF_SPHERE, out.spheres.size());
+                PushSphere(baked[i]);
+            }
         } else if (type == RT_LEAF_MOVING) {
             first = out.moving.size();
             for (int i : ids) PushMoving(baked[i]);
         } else {
             first = out.quads.size();
-            for (int i : ids) PushQuad(baked[i]);
+            for (int i : ids) {
+                hitOfBaked[i] = RT_HIT_MAKE(RT_LEAF_QUAD, out.quads.size());
+                PushQuad(baked[i]);
+            }
         }
         if (first + ids.size() > (size_t)RT_MAX_PRIMS_PER_TYPE) throw std::invalid_argument("too many primitives");
         return RT_REF_MAKE_LEAF(type, first, ids.size());
@@ -760,6 +771,8 @@ struct Packer {
             if (baked.back().type == RT_LEAF_MOVING) out.features |= RT_FEAT_MOVING;
             if (baked.back().type == RT_LEAF_QUAD) out.features |= RT_FEAT_QUAD;
         }
+
+        hitOfBaked.assign(baked.size(), RT_HIT_NONE);
 
         // media: boundary prims go straight to the device arrays (not in the BVH)
         struct Med {
@@ -1000,6 +1013,7 @@ struct Packer {
             out.nodes.assign(2, DevNode{});
             out.root_ref = 0xffffffffu; // RT_TRAV_DONE: the walk loop does not run
             out.max_depth = 0;
+            PackLights();
             return;
         }
         int root;
@@ -1058,6 +1072,44 @@ struct Packer {
             }
         }
         out.root_ref = out.nodes[0].ref;
+        PackLights();
+    }
+
+    // Sampling targets of RT_FLAG_IMPORTANCE: every quad / sphere of a surface object whose material is a DiffuseLight,
+    // in primitive order (the order the oracle lists them in).  Called when every run has been emitted.
+    void PackLights()
+    {
+        std::vector<std::pair<int, DevLight>> found;
+        for (int o = 0; o < d.n_objects; ++o) {
+            const rt_object& ob = d.objects[o];
+            if (ob.kind == RT_OBJ_MEDIUM) continue;
+            for (int k = 0; k < ob.prim_count; ++k) {
+                const int i = ob.first_prim + k;
+                const Baked& bk = baked[i];
+                if ((bk.type != RT_LEAF_QUAD && bk.type != RT_LEAF_SPHERE) || d.materials[bk.material].type != RT_MAT_DIFFUSE_LIGHT)
+                    continue;
+                if (hitOfBaked[i] == RT_HIT_NONE) throw std::invalid_argument("internal: light primitive was not emitted");
+                DevLight l;
+                std::memset(&l, 0, sizeof l);
+                for (int a = 0; a < 3; ++a) {
+                    l.a[a] = bk.a[a];
+                    l.b[a] = bk.type == RT_LEAF_QUAD ? bk.b[a] : (a == 0 ? bk.radius : 0.0);
+                    l.c[a] = bk.type == RT_LEAF_QUAD ? bk.c[a] : 0.0;
+                }
+                l.hit = hitOfBaked[i];
+                if (bk.type == RT_LEAF_QUAD) {
+                    const double* u = bk.b;
+                    const double* v = bk.c;
+                    const double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+                    l.area = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+                }
+                found.emplace_back(i, l);
+            }
+        }
+        std::sort(found.begin(), found.end(), [](const std::pair<int, DevLight>& x, const std::pair<int, DevLight>& y) {
+            return x.first < y.first;
+        });
+        for (const std::pair<int, DevLight>& f : found) out.lights.push_back(f.second);
     }
 };
 

@@ -154,6 +154,8 @@ template <bool SMEM> struct SceneView {
     const DevPerlin* perlins;
     const DevImage* images;
     const DevUvFrame* uv_frames;
+    const DevLight* lights; // RT_FLAG_IMPORTANCE: sampling targets
+    int n_lights;
     const uint8_t* arena;
     uint32_t root_ref;
     const uint32_t* hoisted; // leaf refs every ray tests before it enters the tree (global memory: a uniform load)
@@ -1106,6 +1108,106 @@ RT_DEV d3 RandomInUnitSphere(const StreamKey& key)
 
 RT_DEV d3 Reflect(d3 v, d3 n) { return v - (2.0 * dot(v, n)) * n; } // Vec3.h:122-125
 
+// ------------------------------------------------------ importance sampling
+// RT_FLAG_IMPORTANCE (phase 4 of the reference's roadmap, README.md:37-42 -- PDFs, mixture density,
+// sampling of lights, orthonormal basis -- which the reference does not implement).  The machinery is the one of
+// "Ray Tracing: The Rest of Your Life" (quad::pdf_value / random, sphere::pdf_value / random, onb, mixture_pdf),
+// applied to the scattering the reference has: its Lambertian sends the ray to N + (point in the unit ball)
+// (Material.h:68-86), a direction density of 2 cos^3(theta) / pi, weighed with the albedo alone; Isotropic
+// (Material.h:151-162) is uniform, 1 / 4 pi.  A diffuse bounce draws from
+//     1/2 (that density) + 1/2 (density of the directions towards the lights)
+// and carries (scattering density) / (mixture density): the same image in expectation, less noise wherever the
+// lights are small.  Restated in FP64 by oracle/rt_oracle.cpp ScatterImportance (the parity target).
+//
+// Density with which LightDirection produces `dir` from `o` (book 3: pdf_value); 0 when the ray misses the light.
+template <int FEAT, bool SMEM>
+RT_DEV double LightPdf(const SceneView<SMEM>& sv, const DevLight* l, const d3& o, const d3& dir, double len2)
+{
+    const uint32_t hit = __ldg(&l->hit), index = RT_HIT_INDEX(hit);
+    Ray r;
+    r.o = o;
+    r.d = dir;
+    r.time = 0.0f;
+    if ((FEAT & RT_FEAT_QUAD) && RT_HIT_TYPE(hit) == RT_LEAF_QUAD) {
+        float al, be;
+        if (HitQuad<SMEM, double>(sv, index, r, 0.001, 3.402823466e+38f, al, be) == RT_MISS) return 0.0;
+        const double t = RefineQuadT<SMEM>(sv, index, r);
+        const double2 q2 = LdD2<SMEM>(sv.quads, index * 96u + 32u);
+        const double nz = LdD2<SMEM>(sv.quads, index * 96u + 48u).x;
+        const double cosine = fabs(fma(q2.x, dir.x, fma(q2.y, dir.y, nz * dir.z))) * RsqrtD(len2);
+        return t * t * len2 / (cosine * __ldg(&l->area));
+    }
+    if (RT_HIT_TYPE(hit) != RT_LEAF_SPHERE) return 0.0;
+    if (HitSphere<SMEM, double>(sv, index, r, len2, RcpApprox((float)len2), 0.001, 3.402823466e+38f) == RT_MISS) return 0.0;
+    const double cx = __ldg(&l->a[0]) - o.x, cy = __ldg(&l->a[1]) - o.y, cz = __ldg(&l->a[2]) - o.z;
+    const double radius = __ldg(&l->b[0]);
+    const double cosMax = SqrtD(1.0 - radius * radius * RcpD(fma(cx, cx, fma(cy, cy, cz * cz))));
+    return RcpD(6.283185307179586 * (1.0 - cosMax));
+}
+
+// A direction from `o` towards light `l` (book 3: quad::random; sphere::random = onb + random_to_sphere).
+RT_DEV d3 LightDirection(const DevLight* l, const d3& o, double r1, double r2)
+{
+    const d3 a = make_d3(__ldg(&l->a[0]), __ldg(&l->a[1]), __ldg(&l->a[2]));
+    const d3 b = make_d3(__ldg(&l->b[0]), __ldg(&l->b[1]), __ldg(&l->b[2]));
+    if (RT_HIT_TYPE(__ldg(&l->hit)) == RT_LEAF_QUAD) {
+        const d3 c = make_d3(__ldg(&l->c[0]), __ldg(&l->c[1]), __ldg(&l->c[2]));
+        return make_d3(fma(r2, c.x, fma(r1, b.x, a.x)) - o.x, fma(r2, c.y, fma(r1, b.y, a.y)) - o.y,
+                       fma(r2, c.z, fma(r1, b.z, a.z)) - o.z);
+    }
+    const d3 dir = a - o;
+    const double dist2 = dot(dir, dir);
+    const d3 w = RsqrtD(dist2) * dir;
+    // onb: a = |w.x| > 0.9 ? y : x; v = unit(w x a); u = w x v
+    d3 v = fabs(w.x) > 0.9 ? make_d3(-w.z, 0.0, w.x) : make_d3(0.0, w.z, -w.y);
+    v = RsqrtD(dot(v, v)) * v;
+    const d3 u = make_d3(w.y * v.z - w.z * v.y, w.z * v.x - w.x * v.z, w.x * v.y - w.y * v.x);
+    const double z = 1.0 + r2 * (SqrtD(1.0 - b.x * b.x * RcpD(dist2)) - 1.0);
+    double sn, cs;
+    sincospi(2.0 * r1, &sn, &cs);
+    const double rad = SqrtD(1.0 - z * z);
+    return (cs * rad) * u + ((sn * rad) * v + z * w);
+}
+
+// Lambertian / Isotropic under RT_FLAG_IMPORTANCE.  The four draws (strategy, light, two for the point on it) are
+// block 0 of the bounce's own keyed domain (32), so the sequential ball draws of domain 0 keep their positions.
+// Returns false when the direction carries nothing.
+template <int FEAT, bool SMEM>
+RT_DEV bool ScatterImportance(const SceneView<SMEM>& sv, const Hit& h, bool lambertian, const StreamKey& rng, d3& dir, float& weight)
+{
+    const rt_u4 k = rt_rng_block(rng.seed, rng.pixel, rng.sample, rng.slot, 32u, 0u);
+    const int nLights = sv.n_lights;
+    if (nLights > 0 && rt_bits_to_u01(k.x) < 0.5f) {
+        int li = (int)((double)rt_bits_to_u01(k.y) * (double)nLights);
+        if (li > nLights - 1) li = nLights - 1;
+        dir = LightDirection(&sv.lights[li], h.p, (double)rt_bits_to_u01(k.z), (double)rt_bits_to_u01(k.w));
+    } else {
+        const d3 ball = RandomInUnitSphere(rng);
+        if (lambertian) {
+            dir = h.n + ball;
+            if (fabs(dir.x) < 1e-8 && fabs(dir.y) < 1e-8 && fabs(dir.z) < 1e-8) dir = h.n;
+        } else {
+            dir = RsqrtD(dot(ball, ball)) * ball;
+        }
+    }
+    const double len2 = dot(dir, dir);
+    if (!(len2 > 0.0)) return false;
+    double pMat = 0.07957747154594767; // 1 / 4 pi
+    if (lambertian) {
+        const double c = dot(dir, h.n) * RsqrtD(len2);
+        pMat = c > 0.0 ? 0.6366197723675814 * c * c * c : 0.0; // 2 cos^3 / pi
+    }
+    double pdf = pMat;
+    if (nLights > 0) {
+        double pLight = 0.0;
+        for (int i = 0; i < nLights; ++i) pLight += LightPdf<FEAT, SMEM>(sv, &sv.lights[i], h.p, dir, len2);
+        pdf = 0.5 * (pLight / (double)nLights) + 0.5 * pMat;
+    }
+    if (!(pMat > 0.0) || !(pdf > 0.0)) return false;
+    weight = (float)(pMat / pdf);
+    return true;
+}
+
 // Returns false when the path ends (light, or absorbed by metal).  On true,
 // `dir` is the scattered direction (not normalised, like the reference) and
 // `atten` the attenuation.  `emitted` is Material::Emitted (black unless light).
@@ -1125,6 +1227,14 @@ RT_DEV bool Scatter(const SceneView<SMEM>& sv, const Hit& h, const d3& dirIn, do
     f3 colour = make_f3(m0.x, m0.y, m0.z);
     if ((FEAT & RT_FEAT_TEXTURE) && tex >= 0 && type != RT_MAT_METAL && type != RT_MAT_DIELECTRIC)
         colour = TextureValue<FEAT, SMEM>(sv, tex, h, sphereLike);
+    if constexpr ((FEAT & RT_FEAT_IMPORTANCE) != 0) {
+        if (type == RT_MAT_LAMBERTIAN || type == RT_MAT_ISOTROPIC) {
+            float weight = 0.0f;
+            if (!ScatterImportance<FEAT, SMEM>(sv, h, type == RT_MAT_LAMBERTIAN, rng, dir, weight)) return false;
+            atten = weight * colour;
+            return true;
+        }
+    }
     // Lambertian, Metal and Isotropic all start with RandomInUnitSphere from the top of the slot's stream
     // (Material.h:75,157, Metal.h:27): ONE rejection loop serves the three, instead of one copy per material that
     // the lanes of a warp would run one after the other.
