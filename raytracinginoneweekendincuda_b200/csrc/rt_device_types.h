@@ -79,16 +79,20 @@ struct RT_ALIGN(16) DevMovingSphere {
 };
 
 // ---- Quad (reference Quad.h:25-37): 96 bytes.  Plane (n, D) in FP64 so that
-// t = (D - n.O)/(n.d) does not lose the origin's position on the plane.
+// t = (D - n.O)/(n.d) does not lose the origin's position on the plane.  The interior coordinates of Quad.h:72-73,
+// alpha = w.(p x v) and beta = w.(u x p) with p the hit point relative to Q, are triple products: alpha = p.(v x w),
+// beta = p.(w x u).  The two constant vectors are formed once on the host (FP64, rounded to fp32), so a test costs two
+// dot products instead of two cross products and two dot products.
 struct RT_ALIGN(16) DevQuad {
     double qx, qy, qz;
     double D;
     double nx, ny, nz;
-    float wx, wy, wz;
-    float ux, uy, uz;
-    float vx, vy, vz;
+    float ax, ay, az; // v x w
+    float bx, by, bz; // w x u
     int32_t material;
+    int32_t _p[3];
 };
+static_assert(sizeof(DevQuad) == 96, "DevQuad layout");
 
 // ---- Box: the six quads MakeBox builds (reference Instance.h:166-184), possibly under Translate / RotateY -- any
 // closed parallelepiped of six quads.  128 bytes.  The reference tests the six quads one after the other

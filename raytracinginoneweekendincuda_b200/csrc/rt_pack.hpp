@@ -510,15 +510,13 @@ struct Packer {
         q.ny = n[1] / len;
         q.nz = n[2] / len;
         q.D = q.nx * b.a[0] + q.ny * b.a[1] + q.nz * b.a[2];
-        q.wx = (float)(n[0] / nn);
-        q.wy = (float)(n[1] / nn);
-        q.wz = (float)(n[2] / nn);
-        q.ux = (float)u[0];
-        q.uy = (float)u[1];
-        q.uz = (float)u[2];
-        q.vx = (float)v[0];
-        q.vy = (float)v[1];
-        q.vz = (float)v[2];
+        const double w[3] = {n[0] / nn, n[1] / nn, n[2] / nn}; // Quad.h:36
+        q.ax = (float)(v[1] * w[2] - v[2] * w[1]); // v x w
+        q.ay = (float)(v[2] * w[0] - v[0] * w[2]);
+        q.az = (float)(v[0] * w[1] - v[1] * w[0]);
+        q.bx = (float)(w[1] * u[2] - w[2] * u[1]); // w x u
+        q.by = (float)(w[2] * u[0] - w[0] * u[2]);
+        q.bz = (float)(w[0] * u[1] - w[1] * u[0]);
         q.material = b.material;
         out.quads.push_back(q);
     }

@@ -319,24 +319,21 @@ RT_DEV float HitQuad(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, TM
     const double2 q0 = LdD2<SMEM>(sv.quads, off);        // qx qy
     const double2 q1 = LdD2<SMEM>(sv.quads, off + 16u);  // qz D
     const double2 q2 = LdD2<SMEM>(sv.quads, off + 32u);  // nx ny
-    const double2 q3 = LdD2<SMEM>(sv.quads, off + 48u);  // nz | wx wy
+    const double2 q3 = LdD2<SMEM>(sv.quads, off + 48u);  // nz | ax ay
     const double nz = q3.x;
     const double denom = fma(q2.x, r.d.x, fma(q2.y, r.d.y, nz * r.d.z));
     if (fabs(denom) < 1e-8) return RT_MISS;
     const double num = q1.y - fma(q2.x, r.o.x, fma(q2.y, r.o.y, nz * r.o.z));
     const float t = (float)num * RcpApprox((float)denom);
     if ((TM)t < tmin || t > tmax) return RT_MISS;
-    const float4 q4 = Ld4<SMEM>(sv.quads, off + 64u); // wz ux uy uz   (after wx wy in q3.y)
-    const float4 q5 = Ld4<SMEM>(sv.quads, off + 80u); // vx vy vz mat
-    const float wx = __int_as_float(__double2loint(q3.y)), wy = __int_as_float(__double2hiint(q3.y));
-    const f3 w = make_f3(wx, wy, q4.x);
-    const f3 u = make_f3(q4.y, q4.z, q4.w);
-    const f3 v = make_f3(q5.x, q5.y, q5.z);
+    const float4 q4 = Ld4<SMEM>(sv.quads, off + 64u); // az bx by bz   (after ax ay in q3.y)
+    const float ax = __int_as_float(__double2loint(q3.y)), ay = __int_as_float(__double2hiint(q3.y));
     const double td = (double)t;
     const f3 planar = make_f3((float)(fma(td, r.d.x, r.o.x) - q0.x), (float)(fma(td, r.d.y, r.o.y) - q0.y),
                               (float)(fma(td, r.d.z, r.o.z) - q1.x));
-    const float al = dot(w, cross(planar, v));
-    const float be = dot(w, cross(u, planar));
+    // Quad.h:72-73 as triple products: alpha = p.(v x w), beta = p.(w x u)
+    const float al = dot(planar, make_f3(ax, ay, q4.x));
+    const float be = dot(planar, make_f3(q4.y, q4.z, q4.w));
     if (!(0.0f <= al && al <= 1.0f) || !(0.0f <= be && be <= 1.0f)) return RT_MISS;
     alpha = al;
     beta = be;
@@ -431,8 +428,12 @@ RT_DEV bool BoxSpan(const SceneView<SMEM>& sv, uint32_t index, const Ray& r, dou
         }
         const double inv = RcpD(den);
         const double ta = (lo[p] - s) * inv, tb = (hi[p] - s) * inv;
-        t1 = fmax(t1, fmin(ta, tb));
-        t2 = fmin(t2, fmax(ta, tb));
+        // (explicit compare-and-select: fmin / fmax of doubles carry NaN handling, ~8 instructions each -- ncu put these
+        // two lines at 11 % of the Cornell-smoke kernel's instructions)
+        const bool asc = ta < tb;
+        const double tn = asc ? ta : tb, tf = asc ? tb : ta;
+        t1 = tn > t1 ? tn : t1;
+        t2 = tf < t2 ? tf : t2;
     }
     return t1 <= t2;
 }
@@ -591,18 +592,14 @@ RT_DEV void FinalizeHit(const SceneView<SMEM>& sv, const Ray& r, double a, uint3
         const double2 q2 = LdD2<SMEM>(sv.quads, off + 32u);
         const double2 q3 = LdD2<SMEM>(sv.quads, off + 48u);
         const float4 q4 = Ld4<SMEM>(sv.quads, off + 64u);
-        const float4 q5 = Ld4<SMEM>(sv.quads, off + 80u);
         const double td = RefineQuadT<SMEM>(sv, index, r);
         h.p.x = fma(td, r.d.x, r.o.x);
         h.p.y = fma(td, r.d.y, r.o.y);
         h.p.z = fma(td, r.d.z, r.o.z);
-        const f3 w = make_f3(__int_as_float(__double2loint(q3.y)), __int_as_float(__double2hiint(q3.y)), q4.x);
-        const f3 u = make_f3(q4.y, q4.z, q4.w);
-        const f3 v = make_f3(q5.x, q5.y, q5.z);
         const f3 planar = make_f3((float)(h.p.x - q0.x), (float)(h.p.y - q0.y), (float)(h.p.z - q1.x));
-        h.u = dot(w, cross(planar, v));
-        h.v = dot(w, cross(u, planar));
-        h.material = __float_as_int(q5.w);
+        h.u = dot(planar, make_f3(__int_as_float(__double2loint(q3.y)), __int_as_float(__double2hiint(q3.y)), q4.x));
+        h.v = dot(planar, make_f3(q4.y, q4.z, q4.w));
+        h.material = LdI<SMEM>(sv.quads, off + 80u);
         SetFaceNormal(h, r.d, make_d3(q2.x, q2.y, q3.x));
     } else if ((FEAT & RT_FEAT_MOVING) && type == RT_LEAF_MOVING) {
         double radius;
@@ -661,8 +658,8 @@ RT_MEDIUM_FN bool HitMedium(const SceneView<SMEM>& sv, uint32_t index, const Ray
         const double sq = SqrtD(disc);
         const double q = b > 0.0 ? -(b + sq) : (sq - b); // the root pair without cancellation: q/a and cc/q
         const double ta = q * RcpD(a), tb = cc * RcpD(q);
-        t1 = fmin(ta, tb);
-        t2 = fmax(ta, tb);
+        t1 = ta < tb ? ta : tb;
+        t2 = ta < tb ? tb : ta;
         if (!(t2 > t1 + 0.0001)) return false;
     } else if ((FEAT & RT_FEAT_QUAD) && RT_REF_TYPE(bref) == RT_LEAF_BOX && RT_REF_COUNT(bref) == 1u) {
         // A box as the boundary (the smoke boxes of the Cornell scene, kernel.cu:424-431): entry and exit of one slab test.
