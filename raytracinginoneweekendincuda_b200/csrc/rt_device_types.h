@@ -20,6 +20,13 @@
 #define RT_ALIGN(n) alignas(n)
 #endif
 
+// RT_BVH4 (build option, A/B only -- VERDICT r1 #3): the binary SAH tree collapsed into nodes of up to four children
+// (four adjacent DevNode records = 128 bytes per visit; an unused slot has a negative half-extent and never hits).
+// Measured against the binary tree and not shipped: DESIGN.md 5.4, profiles/r2_ab_w.jsonl.
+#ifndef RT_BVH4
+#define RT_BVH4 0
+#endif
+
 // ---- BVH node: 32 bytes = two 128-bit loads.  Children of an internal node
 // are adjacent (index c and c+1), so one step fetches 64 contiguous bytes.
 // The box is stored as centre and half-extent: the slab test then needs no

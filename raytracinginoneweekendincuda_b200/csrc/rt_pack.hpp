@@ -1053,6 +1053,57 @@ struct Packer {
         };
         std::vector<Todo> stack;
         stack.push_back(Todo{root, 0});
+#if RT_BVH4
+        // A/B build: every internal node adopts its grandchildren (largest box first) until it has four children.
+        // Stack levels: a visit leaves up to three siblings parked while the walk descends into the fourth.
+        while (!stack.empty()) {
+            const Todo t = stack.back();
+            stack.pop_back();
+            const BuildNode& bn = b.nodes[t.node];
+            PackBox(bn.box, out.nodes[t.slot]);
+            out.nodes[t.slot].aux = 0;
+            if (bn.left < 0) {
+                out.nodes[t.slot].ref = leafRef(bn);
+                continue;
+            }
+            std::vector<int> kids = {bn.left, bn.right};
+            while (kids.size() < 4) {
+                int best = -1;
+                for (size_t k = 0; k < kids.size(); ++k)
+                    if (b.nodes[kids[k]].left >= 0 && (best < 0 || b.nodes[kids[k]].box.Area() > b.nodes[kids[best]].box.Area()))
+                        best = (int)k;
+                if (best < 0) break;
+                const int gone = kids[best];
+                kids[best] = b.nodes[gone].left;
+                kids.insert(kids.begin() + best + 1, b.nodes[gone].right);
+            }
+            const int quad = (int)out.nodes.size();
+            out.nodes.resize(out.nodes.size() + 4);
+            out.nodes[t.slot].ref = (uint32_t)quad;
+            for (int k = 0; k < 4; ++k) {
+                DevNode& e = out.nodes[quad + k];
+                std::memset(&e, 0, sizeof e);
+                e.e[0] = e.e[1] = e.e[2] = -1.0f; // empty slot: exit before entry on every axis
+                e.ref = RT_REF_MAKE_LEAF(RT_LEAF_SPHERE, 0, 1);
+            }
+            for (int k = (int)kids.size() - 1; k >= 0; --k) stack.push_back(Todo{kids[k], quad + k});
+        }
+        {
+            // worst-case stack use: depth in collapsed nodes, three parked siblings per level
+            struct Walk {
+                static int Depth4(const std::vector<DevNode>& n, uint32_t ref)
+                {
+                    if (ref & RT_REF_LEAF) return 0;
+                    int d = 0;
+                    for (int k = 0; k < 4; ++k)
+                        if (n[ref + k].e[0] >= 0.0f) d = std::max(d, Depth4(n, n[ref + k].ref));
+                    return d + 1;
+                }
+            };
+            out.max_depth = 3 * Walk::Depth4(out.nodes, out.nodes[0].ref) + 1;
+            if (out.max_depth > 29) throw std::invalid_argument("BVH4 deeper than the traversal stack");
+        }
+#else
         while (!stack.empty()) {
             const Todo t = stack.back();
             stack.pop_back();
@@ -1069,6 +1120,7 @@ struct Packer {
                 stack.push_back(Todo{bn.left, pair}); // left is laid out (and its leaves emitted) first
             }
         }
+#endif
         out.root_ref = out.nodes[0].ref;
         PackLights();
     }

@@ -782,6 +782,46 @@ template <> RT_DEV void LoadPair<false>(const SceneView<false>& sv, uint32_t ref
     hi1 = Ld4<false>(sv.nodes, off + 48u);
 }
 
+#if RT_BVH4
+// A/B build (rt_device_types.h RT_BVH4): one collapsed node = four children, 8 x 128-bit loads, four slab tests, the hits
+// ordered by entry distance with a five-exchange network, the nearest entered and the others parked far-to-near.
+template <bool SMEM>
+RT_DEV void TraceBox(const SceneView<SMEM>& sv, const RaySlab& slab, float tmin, const Stack& stack, Trav& tv, uint32_t& nodeTests)
+{
+    float4 lo0, hi0, lo1, hi1, lo2, hi2, lo3, hi3;
+    LoadPair<SMEM>(sv, tv.ref, lo0, hi0, lo1, hi1);
+    LoadPair<SMEM>(sv, tv.ref + (SMEM || sv.nodes_shared ? 64u : 2u), lo2, hi2, lo3, hi3); // shared address | node index
+    nodeTests += 4;
+    const float inf = 3.402823466e+38f;
+    float e0, e1, e2, e3;
+    if (!SlabEntry(lo0, hi0, slab, tmin, tv.t, e0)) e0 = inf;
+    if (!SlabEntry(lo1, hi1, slab, tmin, tv.t, e1)) e1 = inf;
+    if (!SlabEntry(lo2, hi2, slab, tmin, tv.t, e2)) e2 = inf;
+    if (!SlabEntry(lo3, hi3, slab, tmin, tv.t, e3)) e3 = inf;
+    uint32_t r0 = (uint32_t)__float_as_int(lo0.w), r1 = (uint32_t)__float_as_int(lo1.w);
+    uint32_t r2 = (uint32_t)__float_as_int(lo2.w), r3 = (uint32_t)__float_as_int(lo3.w);
+#define RT_CSWAP(ea, eb, ra, rb)                   \
+    {                                              \
+        const bool s_ = eb < ea;                   \
+        const float lo_ = fminf(ea, eb), hi_ = fmaxf(ea, eb); \
+        const uint32_t a_ = s_ ? rb : ra, b_ = s_ ? ra : rb;  \
+        ea = lo_, eb = hi_, ra = a_, rb = b_;      \
+    }
+    RT_CSWAP(e0, e1, r0, r1)
+    RT_CSWAP(e2, e3, r2, r3)
+    RT_CSWAP(e0, e2, r0, r2)
+    RT_CSWAP(e1, e3, r1, r3)
+    RT_CSWAP(e1, e2, r1, r2)
+#undef RT_CSWAP
+    if (e3 < inf) TravPush(stack, tv, r3);
+    if (e2 < inf) TravPush(stack, tv, r2);
+    if (e1 < inf) TravPush(stack, tv, r1);
+    if (e0 < inf)
+        tv.ref = r0;
+    else
+        TravPop(stack, tv);
+}
+#else
 // One internal node: both children boxes tested, nearer one entered first.
 template <bool SMEM>
 RT_DEV void TraceBox(const SceneView<SMEM>& sv, const RaySlab& slab, float tmin, const Stack& stack, Trav& tv, uint32_t& nodeTests)
@@ -803,6 +843,7 @@ RT_DEV void TraceBox(const SceneView<SMEM>& sv, const RaySlab& slab, float tmin,
         TravPop(stack, tv);
     }
 }
+#endif
 
 // One leaf: a typed run of primitives, or a medium.
 template <int FEAT, bool SMEM>
