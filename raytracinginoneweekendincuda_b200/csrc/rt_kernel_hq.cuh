@@ -28,6 +28,11 @@ namespace {
 
 template <int FEAT> constexpr bool kHqWalkUnroll = RT_HQ_WALK_UNROLL == 2 || (RT_HQ_WALK_UNROLL == 1 && !(FEAT & RT_FEAT_TEXTURE_HEAVY));
 
+#ifndef RT_HQ_BOX_STEPS
+#define RT_HQ_BOX_STEPS 3 /* box steps per leaf step of the unrolled walk loop: 2, 3 or 4.  Measured (64 spp, Grays/s; Book 1 4K /
+                              scene 0 / scene 7): 2: 21.51 / 14.38 / 19.29, 3: 21.78 / 14.75 / 19.30, 4: 21.56 / 14.62 / 19.32 */
+#endif
+
 #ifndef RT_HQ_STACKED_HOIST
 #define RT_HQ_STACKED_HOIST 1 /* build option (A/B): hoisted items through the walk loop's leaf step (BeginWalkStacked):
                                  0 never, 1 the feature-complete kernel, 2 every kernel */
@@ -179,19 +184,26 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
                 }
                 ++nRays;
             }
-            // One turn of the loop = two box steps, then one leaf step.  A lane that reaches a leaf waits for the leaf
-            // step (the FP64 primitive tests then run for every lane that piled up in the two steps before); a lane
-            // that is done (RT_TRAV_DONE has the leaf bit and is excluded) idles until the slowest walk ends.  Same
-            // schedule as the `step & 1` leaf turn of the other kernels, without the step counter and with the loop
-            // test, the reconvergence point and the branch paid once per two box steps instead of once per step.
-            // Measured (4K Book 1 / scene 0 / 7 / 8 / 9, 64 spp): +0.2 / +1.8 / +8.3 / +0.5 / -6.9 % -- a gain wherever the
-            // kernel is small, a loss for the feature-complete instantiation (its code no longer fits the instruction
-            // cache as it is), so that one keeps the plain loop.
+            // One turn of the loop = RT_HQ_BOX_STEPS (three) box steps, then one leaf step.  A lane that reaches a leaf waits
+            // for the leaf step (the FP64 primitive tests then run for every lane that piled up in the box steps before); a
+            // lane that is done (RT_TRAV_DONE has the leaf bit and is excluded) idles until the slowest walk ends.  Same
+            // schedule as the `step & mask` leaf turn of the other kernels, without the step counter and with the loop
+            // test, the reconvergence point and the branch paid once per three box steps instead of once per step.
+            // Measured, two box steps against the plain loop (4K Book 1 / scene 0 / 7 / 8 / 9, 64 spp): +0.2 / +1.8 / +8.3 /
+            // +0.5 / -6.9 % -- a gain wherever the kernel is small, a loss for the feature-complete instantiation (its
+            // code does not fit the instruction cache as it is; measured again after it shrank: -5 %), so that one keeps
+            // the plain loop.  Three steps against two: +1.3 % Book 1, +2.6 % scene 0.
             if constexpr (kHqWalkUnroll<FEAT>) {
             while (tv.ref != RT_TRAV_DONE) {
                 uint32_t nodeTests = 0, primTests = 0;
                 if (!(tv.ref & RT_REF_LEAF)) TraceBox<SMEM>(sv, slab, 0.001f, stack, tv, nodeTests);
                 if (!(tv.ref & RT_REF_LEAF)) TraceBox<SMEM>(sv, slab, 0.001f, stack, tv, nodeTests);
+#if RT_HQ_BOX_STEPS >= 3 /* (profiles/r2_ab_y.jsonl) */
+                if (!(tv.ref & RT_REF_LEAF)) TraceBox<SMEM>(sv, slab, 0.001f, stack, tv, nodeTests);
+#endif
+#if RT_HQ_BOX_STEPS >= 4
+                if (!(tv.ref & RT_REF_LEAF)) TraceBox<SMEM>(sv, slab, 0.001f, stack, tv, nodeTests);
+#endif
                 if ((tv.ref & RT_REF_LEAF) && tv.ref != RT_TRAV_DONE)
                     TraceLeaf<FEAT, SMEM>(sv, ray, a, slab.rcpA, 0.001f, stack, tv, args.seed, pixel, sample, bounce + 1u,
                                           primTests);
