@@ -622,7 +622,7 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
         // the largest block whose stacks + queues still leave room for the scene in shared memory
         // (if none does, the scene stays in global memory and the block is as large as registers allow)
         threads = maxThreads;
-        for (int cand = maxThreads; cand >= 384; cand -= 64)
+        for (int cand = maxThreads; cand >= 384; cand -= 32)
             if ((size_t)cand * 4 * stackLevels + (size_t)(cand / 32) * warpBytes + 16 + h->stagedBytes <= (size_t)d.maxSmemOptin) {
                 threads = cand;
                 break;
@@ -632,7 +632,7 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
     bool nodesOnly = false;
     if (hitQueue && !(p->flags & (RT_FLAG_SCENE_IN_GLOBAL | RT_FLAG_NODES_IN_GLOBAL)) &&
         (size_t)threads * 4 * stackLevels + (size_t)(threads / 32) * warpBytes + 16 + h->stagedBytes > (size_t)d.maxSmemOptin) {
-        for (int cand = p->block_threads > 0 ? threads : maxThreads; cand >= std::max(512, maxThreads - 128); cand -= 64) {
+        for (int cand = p->block_threads > 0 ? threads : maxThreads; cand >= std::max(512, maxThreads - 128); cand -= 32) {
             if ((size_t)cand * 4 * stackLevels + (size_t)(cand / 32) * warpBytes + 32 + a.nodesBytes <= (size_t)d.maxSmemOptin) {
                 threads = cand;
                 nodesOnly = true;

@@ -125,7 +125,17 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
 constexpr int MegaMaxThreads(int feat) { return feat == 0 ? 768 : 512; }
 // The head/tail kernel holds no path state across rounds: with moving spheres and checker textures it
 // still fits 80 registers (768 threads); the feature-complete instantiation runs at 640.
-constexpr int HtMaxThreads(int feat) { return (feat & ~(RT_FEAT_MOVING | RT_FEAT_TEXTURE)) == 0 ? 768 : 640; }
+// Build options for the A/B.  The register file is per SM sub-partition (16 K registers each), so what counts is the
+// fullest sub-partition: 768 threads = 6 warps each -> 80 registers; 800 or 832 put 7 warps on one -> 72 registers and
+// spills: measured -6.6 % / -8 % on Book 1 (profiles/r2_ab_za.jsonl).  640 = 5 warps each -> 96 registers; 672 / 704 ->
+// 80: -11 % / -14 % on the Book 2 final scene.
+#ifndef RT_HT_THREADS_SMALL
+#define RT_HT_THREADS_SMALL 768
+#endif
+#ifndef RT_HT_THREADS_LARGE
+#define RT_HT_THREADS_LARGE 640
+#endif
+constexpr int HtMaxThreads(int feat) { return (feat & ~(RT_FEAT_MOVING | RT_FEAT_TEXTURE)) == 0 ? RT_HT_THREADS_SMALL : RT_HT_THREADS_LARGE; }
 
 template <int FEAT, bool SMEM, bool STATS>
 __global__ void __launch_bounds__(MegaMaxThreads(FEAT), 1) RenderMega(const DevScene scene, const DevCamera cam, const RenderArgs args)
