@@ -147,3 +147,99 @@ class HandScene:
         cam.vup[:] = [0.0, 1.0, 0.0]
         cam.background[:] = [0.8, 0.9, 1.0]
         return cam
+
+
+class BoxScene:
+    """A scene of MakeBox lists written through the ctypes structs (reference Instance.h:166-184 for the six quads and
+    their order): a GLASS box under RotateY + Translate (rays enter it, travel inside and leave through the exit face), a
+    fuzzy METAL box, a ConstantMedium whose boundary is a rotated box, on a Lambertian ground sphere under a bright sky.
+    Exercises the slab-tested box (csrc/rt_trace.cuh HitBox / BoxSpan) where the built-in scenes do not: hits from inside,
+    two-sided faces, a medium entered from any side."""
+
+    @staticmethod
+    def _box_quads(lo, hi):
+        dx, dy, dz = (hi[0] - lo[0], 0.0, 0.0), (0.0, hi[1] - lo[1], 0.0), (0.0, 0.0, hi[2] - lo[2])
+
+        def neg(v):
+            return tuple(-c for c in v)
+
+        return [((lo[0], lo[1], hi[2]), dx, dy), ((hi[0], lo[1], hi[2]), neg(dz), dy), ((hi[0], lo[1], lo[2]), neg(dx), dy),
+                ((lo[0], lo[1], lo[2]), dz, dy), ((lo[0], hi[1], hi[2]), dx, neg(dz)), ((lo[0], lo[1], lo[2]), dx, dz)]
+
+    def __init__(self):
+        boxes = [  # (lo, hi, degrees, offset, material, medium?)
+            ((-1.0, 0.0, -1.0), (1.0, 2.0, 1.0), 25.0, (0.2, 0.0, 0.3), 1, False),    # glass
+            ((-0.5, 0.0, -0.5), (0.5, 1.5, 0.5), 0.0, (3.0, 0.0, 0.0), 2, False),     # metal, axis-aligned, no instance
+            ((-0.8, 0.0, -1.0), (0.8, 1.5, 1.0), -15.0, (-3.0, 0.0, 0.2), 3, True),   # smoke
+        ]
+        n_prims = 1 + 6 * len(boxes)
+        self.prims = (A.rt_prim * n_prims)()
+        self.xforms = (A.rt_xform * (2 * len(boxes)))()
+        self.objects = (A.rt_object * (1 + len(boxes)))()
+        g = self.prims[0]
+        g.type, g.material, g.radius = A.RT_PRIM_SPHERE, 0, 1000.0
+        g.a[:] = [0.0, -1000.0, 0.0]
+        o = self.objects[0]
+        o.kind, o.first_prim, o.prim_count = A.RT_OBJ_PRIM, 0, 1
+        o.bbox[:] = [-1000, 1000, -2000, 0, -1000, 1000]
+        n_x = 0
+        for b, (lo, hi, deg, off, mat, medium) in enumerate(boxes):
+            first_x, count_x = 0, 0
+            rad = np.radians(deg)
+            s, c = float(np.sin(rad)), float(np.cos(rad))
+            if deg != 0.0:
+                self.xforms[n_x].type = A.RT_XFORM_TRANSLATE  # outermost first: Translate(RotateY(box))
+                self.xforms[n_x].v[:] = list(off)
+                self.xforms[n_x + 1].type = A.RT_XFORM_ROTATE_Y
+                self.xforms[n_x + 1].v[:] = [s, c, deg]
+                first_x, count_x = n_x, 2
+                n_x += 2
+            corners = []
+            for k, (q, u, v) in enumerate(self._box_quads(lo, hi)):
+                p = self.prims[1 + 6 * b + k]
+                p.type, p.material = A.RT_PRIM_QUAD, mat
+                if deg == 0.0:
+                    q = tuple(q[a] + off[a] for a in range(3))  # no instance: the box is built where it stands
+                p.a[:] = list(q)
+                p.b[:] = list(u)
+                p.c[:] = list(v)
+                p.first_xform, p.xform_count = first_x, count_x
+                for i in (0, 1):
+                    for j in (0, 1):
+                        pt = np.array(q) + i * np.array(u) + j * np.array(v)
+                        if deg != 0.0:  # Instance.h:136-147 then the offset
+                            pt = np.array([c * pt[0] + s * pt[2], pt[1], -s * pt[0] + c * pt[2]]) + np.array(off)
+                        corners.append(pt)
+            corners = np.array(corners)
+            ob = self.objects[1 + b]
+            ob.kind = A.RT_OBJ_MEDIUM if medium else A.RT_OBJ_LIST
+            ob.first_prim, ob.prim_count = 1 + 6 * b, 6
+            if medium:
+                ob.phase_material, ob.medium_id, ob.density = 4, 0, 0.8
+            lo_w, hi_w = corners.min(0), corners.max(0)
+            ob.bbox[:] = [lo_w[0], hi_w[0], lo_w[1], hi_w[1], lo_w[2], hi_w[2]]
+        self.n_xforms = n_x
+        self.materials = (A.rt_material * 5)()
+        self.textures = (A.rt_texture * 3)()
+        for t, col in enumerate([(0.5, 0.5, 0.5), (0.1, 0.1, 0.1), (0.9, 0.9, 0.9)]):
+            self.textures[t].type = A.RT_TEX_SOLID
+            self.textures[t].color[:] = list(col)
+        self.materials[0].type, self.materials[0].texture = A.RT_MAT_LAMBERTIAN, 0
+        self.materials[1].type, self.materials[1].ior = A.RT_MAT_DIELECTRIC, 1.5
+        self.materials[2].type, self.materials[2].fuzz = A.RT_MAT_METAL, 0.1
+        self.materials[2].albedo[:] = [0.8, 0.6, 0.2]
+        self.materials[3].type, self.materials[3].texture = A.RT_MAT_LAMBERTIAN, 1  # (boundary quads: never shaded)
+        self.materials[4].type, self.materials[4].texture = A.RT_MAT_ISOTROPIC, 2
+        self._desc = A.rt_scene_desc(abi_version=A.RT_ABI_VERSION, n_objects=1 + len(boxes), n_prims=n_prims,
+                                     n_xforms=n_x, n_materials=5, n_textures=3, objects=self.objects, prims=self.prims,
+                                     xforms=self.xforms, materials=self.materials, textures=self.textures)
+        self.desc = C.pointer(self._desc)
+
+    def camera(self, W, H, spp, max_depth=50):
+        cam = A.rt_camera(image_width=W, image_height=H, samples_per_pixel=spp, max_depth=max_depth, vfov=35.0,
+                          defocus_angle=0.0, focus_dist=10.0, aperture=0.0, time0=0.0, time1=0.0)
+        cam.lookfrom[:] = [0.5, 3.0, 10.0]
+        cam.lookat[:] = [0.0, 1.0, 0.0]
+        cam.vup[:] = [0.0, 1.0, 0.0]
+        cam.background[:] = [0.7, 0.8, 1.0]
+        return cam

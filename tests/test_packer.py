@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import A, HandScene
+from conftest import A, BoxScene, HandScene
 from raytracinginoneweekendincuda_b200 import BuiltinScene
 
 
@@ -54,6 +54,18 @@ def test_closed_six_quad_lists_become_slab_tested_boxes(lib, earth):
     sc = BuiltinScene(9, earth)
     rc, i = pack(lib, sc.desc)
     assert i.n_nodes * 32 < 100 * 1024
+
+
+def test_boxes_under_instances_and_as_medium_boundaries(lib):
+    """conftest.BoxScene: a rotated + translated glass box, a plain metal box, a medium bounded by a rotated box: three
+    DevBox records; the scene is small enough to be tested flat (ground sphere, the two surface boxes, the medium)."""
+    sc = BoxScene()
+    rc, i = pack(lib, sc.desc)
+    assert rc == 0, lib.rt_last_error()
+    assert (i.n_boxes, i.n_quads, i.n_spheres, i.n_media) == (3, 18, 1, 1)
+    assert i.n_hoisted == 3 and [(i.hoisted[k] >> 28) & 7 for k in range(3)] == [0, 4, 3]
+    rc, j = pack(lib, sc.desc, flags=A.RT_UPLOAD_NO_BOXES)
+    assert rc == 0 and j.n_boxes == 0 and j.n_quads == 18
 
 
 def _six_quad_scene(shift_top=0.0, tilt=0.0):

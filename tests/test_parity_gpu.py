@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, A, HandScene, oracle_render, oracle_render_region
+from conftest import ROOT, A, BoxScene, HandScene, oracle_render, oracle_render_region
 from raytracinginoneweekendincuda_b200 import BuiltinScene, Renderer, write_ppm
 
 pytestmark = pytest.mark.gpu
@@ -138,6 +138,22 @@ def test_slab_tested_boxes_do_not_change_the_image(earth, sid, W, H, spp):
     assert abs(int(sa.rays) - int(sb.rays)) <= 1e-4 * sb.rays
     ok = (np.abs(a - b) <= REL_TOL * np.abs(b) + ABS_FLOOR).all(axis=2)
     assert ok.mean() >= 0.9995, f"scene {sid}: {ok.mean() * 100:.3f}% of pixels within 1e-3 of the quad-by-quad render"
+
+
+@pytest.mark.parametrize("upload_flags", [0, A.RT_UPLOAD_NO_BOXES, A.RT_UPLOAD_NO_HOIST])
+def test_glass_metal_and_smoke_boxes_match_the_oracle(oracle, upload_flags):
+    """The slab-tested box where the built-in scenes do not take it (conftest.BoxScene): a glass box under RotateY +
+    Translate (hits from inside: the exit face), a fuzzy metal box, a medium bounded by a rotated box that rays enter
+    from every side -- against the oracle, which tests the six quads one by one in object space as the reference does.
+    With the boxes hoisted (default), kept as quads, and inside the tree."""
+    sc = BoxScene()
+    W, H, spp = 160, 90, 8
+    cam = sc.camera(W, H, spp, 50)
+    want, ost = oracle_render(oracle, sc, cam, 0, spp)
+    got, st, _ = gpu_render(sc, cam, upload_flags=upload_flags)
+    frac = match_fraction(got, want, spp)
+    assert frac >= MIN_MATCH, f"{frac * 100:.3f}% of pixels within 1e-3"
+    assert abs(int(st.rays) - int(ost.rays)) <= 2e-3 * ost.rays
 
 
 @pytest.mark.parametrize("sid,W,H,spp", [(10, 200, 113, 6), (0, 96, 54, 4), (7, 64, 64, 6), (8, 64, 64, 6), (9, 96, 54, 3)])
