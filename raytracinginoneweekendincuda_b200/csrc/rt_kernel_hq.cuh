@@ -21,7 +21,7 @@
 #include "rt_kernels.cuh"
 
 #ifndef RT_HQ_WALK_UNROLL
-#define RT_HQ_WALK_UNROLL 1 /* build option (A/B): two box steps + one leaf step per loop turn: 0 never, 1 small kernels, 2 all */
+#define RT_HQ_WALK_UNROLL 1 /* build option (A/B): RT_HQ_BOX_STEPS box steps + one leaf step per loop turn: 0 never, 1 small kernels, 2 all */
 #endif
 
 namespace {
