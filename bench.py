@@ -375,6 +375,26 @@ def short_frame_e2e(torch, Renderer, local, steps):
             "what": "wall clock around upload + render + readback(srgb8) + free, host buffers"}
 
 
+def host_build_times(reps=5):
+    """what the host does before the path -- validation, instance baking, box recognition, hoisting, the
+    binned-SAH build and packing (csrc/rt_pack.hpp, everything rt_scene_upload does short of the copy) -- timed through
+    the host-only rt_scene_pack_info: best of `reps`, ms, for the headline scene and the largest one."""
+    import ctypes as C
+    from raytracinginoneweekendincuda_b200 import BuiltinScene, _abi as A
+    out = {}
+    for name, sid in (("book1_final (485 primitives)", 10), ("book2_final (3 409 primitives, 400 boxes)", 9)):
+        sc = BuiltinScene(sid, earth_texels() if sid == 9 else None)
+        info, opt = A.rt_pack_info(), A.rt_upload_options()
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            rc = sc.lib.rt_scene_pack_info(sc.desc, C.byref(opt), C.byref(info))
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+        if rc == 0:
+            out[name] = {"ms": round(best, 3), "nodes": info.n_nodes, "boxes": info.n_boxes, "hoisted": info.n_hoisted}
+    return out
+
+
 def run_b200_arm():
     import numpy as np
     import torch
@@ -658,6 +678,7 @@ def run_b200_arm():
             cfgs.append(time_config(torch, Renderer, scn, cfg, local, peak.value))
         line["configs"] = cfgs
         line["e2e_short_frame"] = short_frame_e2e(torch, Renderer, local, max(3, ARGS.steps))
+        line["host_build_ms"] = host_build_times()
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local])
