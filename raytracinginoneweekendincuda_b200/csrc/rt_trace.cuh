@@ -782,6 +782,9 @@ template <> RT_DEV void LoadPair<false>(const SceneView<false>& sv, uint32_t ref
     hi1 = Ld4<false>(sv.nodes, off + 48u);
 }
 
+// (Measured and dropped: a `prefetch.global.L1` of the leaf's first record, issued by the box step that selects the leaf
+// as the next visit, for scenes whose primitives stay in global memory -- Book 2 final 5.22 -> 4.72 Grays/s: ten more
+// instructions per box step cost more than the hidden latency returns.  profiles/r2_ab_zd.jsonl.)
 #if RT_BVH4
 // A/B build (rt_device_types.h RT_BVH4): one collapsed node = four children, 8 x 128-bit loads, four slab tests, the hits
 // ordered by entry distance with a five-exchange network, the nearest entered and the others parked far-to-near.
