@@ -40,6 +40,20 @@ template <int FEAT> constexpr bool kHqWalkUnroll = RT_HQ_WALK_UNROLL == 2 || (RT
 // Measured (64 spp; Book 1 4K / scene 0 / 7 / 8 / 9, Grays/s): never 21.24 / 14.33 / 17.59 / 12.97 / 4.59; every kernel
 // 20.84 / 14.33 / 17.38 / 12.87 / 4.97 (profiles/r2_ab_p.jsonl).  The feature-complete kernel shrinks from 5 344 to
 // 4 048 instructions and gains 8 %; the small kernels lose 1-2 % to the extra loop turns.
+// RT_HQ_BINS: the 64 record slots of a warp as TWO stacks, one from each end -- hits on spheres from the bottom, hits on
+// quads / box faces / media from the top -- and a tail round pops from the fuller one first (the other tops the round
+// up when it holds fewer than 32).  The hit type is in the hit id, so binning costs no load; what it buys is rounds
+// whose lanes shade the same primitive type and start walks of similar length (a ray leaving the ground boxes of the
+// Book 2 final scene escapes in a few steps, one inside the 1000-sphere cluster takes dozens).  Scenes with quads only.
+// Build option, OFF: measured on the B200 with parity green (profiles/r2_ab_ze.jsonl, Grays/s bins vs one stack): simple
+// light 10.89 vs 11.03, Cornell boxes 18.95 vs 19.40, Cornell smoke 14.35 vs 14.64, Book 2 final 5.22 vs 5.24 (1080p) and
+// 6.17 vs 6.21 (4K) -- with 32 to 63 records per warp neither stack is often full enough to fill a round on its own, and
+// the mixed rounds that remain pay for the second ballot.  north_star's "per-material shade queues", tried and not taken.
+#ifndef RT_HQ_BINS
+#define RT_HQ_BINS 0
+#endif
+template <int FEAT> constexpr bool kHqBins = RT_HQ_BINS != 0 && (FEAT & RT_FEAT_QUAD) != 0;
+
 template <int FEAT>
 constexpr bool kHqStackedHoist = RT_HQ_STACKED_HOIST == 2 || (RT_HQ_STACKED_HOIST == 1 && (FEAT & RT_FEAT_TEXTURE_HEAVY) != 0);
 
@@ -89,6 +103,8 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
         SUM[lane] = SUM[32 + lane] = SUM[64 + lane] = 0.0f;
         __syncwarp();
         int nQ = 0;
+        int nTop = 0; // kHqBins: records in the stack that grows down from slot 63 (the other one holds nQ - nTop)
+        (void)nTop;
         int headSample = args.sampleBegin;
 
         while (headSample < args.sampleEnd || nQ > 0) {
@@ -105,8 +121,19 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
                 const int n = min(nQ, 32);
                 const bool on = lane < n;
                 uint32_t hit = 0;
+                int e = nQ - n + lane;
+                if constexpr (kHqBins<FEAT>) {
+                    // the fuller stack first; lanes beyond it take the newest records of the other one
+                    const int nBot = nQ - nTop;
+                    const bool topFirst = nTop > nBot;
+                    const int takeTop = topFirst ? min(n, nTop) : n - min(n, nBot);
+                    const int takeBot = n - takeTop;
+                    const int k = topFirst ? lane : lane - takeBot; // index among the lanes that read the top stack
+                    const bool fromTop = topFirst ? lane < takeTop : lane >= takeBot;
+                    e = fromTop ? kHqQueue - nTop + k : nBot - takeBot + (topFirst ? lane - takeTop : lane);
+                    nTop -= takeTop;
+                }
                 if (on) {
-                    const int e = nQ - n + lane;
                     ray.o = make_d3(QP[e], QP[kHqQueue + e], QP[2 * kHqQueue + e]);
                     ray.d = make_d3(QD[e], QD[kHqQueue + e], QD[2 * kHqQueue + e]);
                     ray.time = (FEAT & RT_FEAT_MOVING) ? QTIME[e] : 0.0f;
@@ -252,8 +279,16 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
             {
                 const bool push = walk && tv.hit != RT_HIT_NONE;
                 const unsigned pm = __ballot_sync(FULL, push);
+                int e = nQ + __popc(pm & ltMask);
+                int pushedTop = 0;
+                if constexpr (kHqBins<FEAT>) {
+                    const uint32_t ht = RT_HIT_TYPE(tv.hit);
+                    const bool toTop = push && ht != RT_LEAF_SPHERE && ht != RT_LEAF_MOVING;
+                    const unsigned tm = __ballot_sync(FULL, toTop);
+                    pushedTop = __popc(tm);
+                    e = toTop ? kHqQueue - 1 - nTop - __popc(tm & ltMask) : (nQ - nTop) + __popc((pm & ~tm) & ltMask);
+                }
                 if (push) {
-                    const int e = nQ + __popc(pm & ltMask);
                     double tHit = (double)tv.t;
                     if ((FEAT & RT_FEAT_MEDIUM) && RT_HIT_TYPE(tv.hit) == RT_LEAF_MEDIUM) tHit = tv.tMedium;
                     QP[e] = fma(tHit, ray.d.x, ray.o.x);
@@ -274,6 +309,7 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
                     }
                 }
                 nQ += __popc(pm);
+                if constexpr (kHqBins<FEAT>) nTop += pushedTop;
                 __syncwarp();
             }
         }
