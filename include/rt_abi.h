@@ -332,7 +332,9 @@ float rt_rng_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t sl
 
 /* Test hook: renders `sample` of the whole frame with the instrumented kernel and
  * returns, for the path of (pixel, sample), one 8-float record per bounce:
- * {hit id bits, t, material bits, front face, p.x, p.y, p.z, 1}; unused records are 0. */
+ * {hit id bits, t, material bits, front face, p.x, p.y, p.z, 1}; unused records are 0.
+ * pixel = -2 (hit-queue kernel): instead, the first 128 words of `records` are uint32 counters -- a histogram of the
+ * child-pair steps per walk of that sample, camera rays in [0, 64), scattered rays in [64, 128) (tools/walk_hist.py). */
 int rt_debug_trace_path(rt_scene_handle scene, const rt_camera* cam, const rt_render_params* p, int32_t pixel,
                         int32_t sample, float* records, int32_t max_records);
 

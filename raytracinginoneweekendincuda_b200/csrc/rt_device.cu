@@ -581,7 +581,7 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
     a.seed = p->seed;
     a.debugPixel = h->debugPixel;
     a.debugSample = h->debugSample;
-    a.debugOut = h->debugPixel >= 0 ? d.debugOut : nullptr;
+    a.debugOut = (h->debugPixel >= 0 || h->debugPixel == -2) ? d.debugOut : nullptr; // -2: walk-length histogram
     // leaf turn every 2nd step (measured best: 1 -> 11.3, 2 -> 11.5, 4 -> 11.2 Grays/s in round 1; again in round 2);
     // development knob in flags bits 4-5: 1 = every step, 2 = every 4th, 3 = every 8th
     static const int kLeafMasks[4] = {1, 0, 3, 7};

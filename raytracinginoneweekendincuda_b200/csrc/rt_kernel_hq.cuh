@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
             // +0.5 / -6.9 % -- a gain wherever the kernel is small, a loss for the feature-complete instantiation (its
             // code does not fit the instruction cache as it is; measured again after it shrank: -5 %), so that one keeps
             // the plain loop.  Three steps against two: +1.3 % Book 1, +2.6 % scene 0.
+            uint32_t walkTests = 0; // STATS: box tests of this lane's walk (histogram hook, rt_debug_trace_path pixel = -2)
+            (void)walkTests;
             if constexpr (kHqWalkUnroll<FEAT>) {
             while (tv.ref != RT_TRAV_DONE) {
                 uint32_t nodeTests = 0, primTests = 0;
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
                 if (STATS) {
                     nNode += nodeTests;
                     nPrim += primTests;
+                    walkTests += nodeTests;
                 }
             }
             } else {
@@ -252,9 +255,12 @@ __global__ void __launch_bounds__(HtMaxThreads(FEAT), 1) RenderHitQueue(const De
                 if (STATS) {
                     nNode += nodeTests;
                     nPrim += primTests;
+                    walkTests += nodeTests;
                 }
             }
             }
+            if (STATS && args.debugOut && args.debugPixel == -2 && walk) // histogram of box-pair steps per walk: heads | tails
+                atomicAdd(reinterpret_cast<unsigned int*>(args.debugOut) + (tailRound ? 64u : 0u) + min(63u, walkTests / 2u), 1u);
             if (walk && tv.hit == RT_HIT_NONE) { // kernel.cu:74-79
                 add = thr * background;
                 hasAdd = true;
