@@ -62,6 +62,24 @@ def test_two_devices_render_the_one_device_frame(earth, flags, path, sid, W, H, 
     assert s3.rays == s1.rays and np.allclose(one, rev, rtol=3e-6, atol=1e-7)
 
 
+def test_two_devices_importance_sampling_equals_one_device():
+    """RT_FLAG_IMPORTANCE through a two-device handle: the light table travels with the arena, the draws are keyed on the
+    global sample index, so the two-device frame is the one-device frame up to fp32 summation order."""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc = BuiltinScene(7)
+    cam = sc.camera(96, 96, 8, 50)
+    out = []
+    for devices in (None, [0, 1]):
+        r = Renderer(sc.desc, devices=devices) if devices else Renderer(sc.desc)
+        r.render(cam, flags=A.RT_FLAG_IMPORTANCE)
+        lin, _, st = r.readback()
+        r.close()
+        out.append((lin, st.rays))
+    assert out[0][1] == out[1][1]
+    assert np.allclose(out[0][0], out[1][0], rtol=3e-6, atol=1e-7)
+
+
 def test_two_devices_accumulate_across_calls():
     """Render, read back (reduce), render more samples, read back again: device 0 keeps the running total, the other
     accumulators restart from zero after each reduction."""
