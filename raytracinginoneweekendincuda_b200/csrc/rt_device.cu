@@ -657,7 +657,17 @@ int LaunchOn(rt_scene_s* h, DeviceCtx& d, const rt_camera* cam, const rt_render_
     const bool wantStats = (p->flags & RT_FLAG_STATS) != 0 || a.debugOut != nullptr;
     const bool smem = !(p->flags & RT_FLAG_SCENE_IN_GLOBAL) &&
                       stackBytes + poolBytes + h->stagedBytes <= (size_t)d.maxSmemOptin / (size_t)blocksPerSm;
-    const size_t smemBytes = stackBytes + poolBytes + (smem ? h->stagedBytes : (nodesOnly ? a.nodesBytes + 16 : 0));
+    size_t smemBytes = stackBytes + poolBytes + (smem ? h->stagedBytes : (nodesOnly ? a.nodesBytes + 16 : 0));
+    // Perlin table 0 beside it when the kernel has noise textures and there is room.  Where the
+    // primitives stay in global memory, stacks, queues and the node table leave L1 ~28 KB, which the 5 KB table (224 loads
+    // per marble hit) shared with every primitive, material and texel fetch: measured on the Book 2 final scene 5.23 ->
+    // 5.57 Grays/s at 1920x1080, 6.19 -> 6.78 at 4K.  Small scenes: 13.3 vs 13.0 (scene 3), 11.1 vs 10.8 (scene 5) against
+    // the same generic loads from global memory (profiles/r2_ab_zf.jsonl).
+    if (hitQueue && (d.dev.features & RT_FEAT_TEXTURE_HEAVY) && !pk.perlins.empty() && !(p->flags & RT_FLAG_SCENE_IN_GLOBAL) &&
+        smemBytes + sizeof(DevPerlin) + 16 <= (size_t)d.maxSmemOptin / (size_t)blocksPerSm) {
+        a.perlinBytes = (uint32_t)sizeof(DevPerlin);
+        smemBytes += sizeof(DevPerlin) + 16;
+    }
     if (smemBytes > (size_t)d.maxSmemOptin) {
         rt_set_error("rt_render: block of %d threads needs %zu B of shared memory (max %d)", threads, smemBytes, d.maxSmemOptin);
         return RT_ERR_INVALID;

@@ -32,6 +32,7 @@ struct RenderArgs {
     float* debugOut; // [max_depth][8]: hit id, t, material, front, p.x, p.y, p.z, 1
     // byte sizes of the staged arrays (SMEM variant)
     uint32_t nodesBytes, spheresBytes, sphereMatBytes, movingBytes, quadsBytes, boxesBytes, mediaBytes, materialsBytes, matParamsBytes;
+    uint32_t perlinBytes; // sizeof(DevPerlin) when Perlin table 0 is staged in shared memory, else 0
     int stageNodesOnly; // scene in global memory, node table staged (SceneView::nodes_shared)
 };
 
@@ -100,6 +101,12 @@ __device__ __forceinline__ SceneView<SMEM> SetupScene(const DevScene& scene, con
     }
     sv.textures = scene.textures;
     sv.perlins = scene.perlins;
+    sv.perlin0 = scene.perlins;
+    if (args.perlinBytes) { // the marble texture's lattice tables (Perlin.h:22-34): 5 KB, 56 x 4 loads per shaded hit
+        const uint32_t at = Stage(cursor, smem, scene.perlins, args.perlinBytes);
+        sv.perlin0 = reinterpret_cast<const DevPerlin*>(smem + at);
+        __syncthreads();
+    }
     sv.images = scene.images;
     sv.uv_frames = scene.uv_frames;
     sv.lights = scene.lights;

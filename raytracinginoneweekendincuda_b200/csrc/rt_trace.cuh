@@ -152,6 +152,7 @@ template <bool SMEM> struct SceneView {
     // never staged: textures and their tables
     const DevTexture* textures;
     const DevPerlin* perlins;
+    const DevPerlin* perlin0; // table 0 staged in shared memory (generic pointer), or perlins: SetupScene
     const DevImage* images;
     const DevUvFrame* uv_frames;
     const DevLight* lights; // RT_FLAG_IMPORTANCE: sampling targets
@@ -907,7 +908,8 @@ template <bool SMEM> RT_DEV void BeginWalkStacked(const SceneView<SMEM>& sv, con
 // ----------------------------------------------------------------- textures
 // Perlin.h:38-139.  Lattice cell and fractions from the FP64 point (octave 6
 // scales it by 64, where fp32 would have lost the fraction); the rest fp32.
-RT_DEV float PerlinNoise(const DevPerlin* __restrict__ t, double px, double py, double pz)
+// (Plain loads, not __ldg: `t` may point at the copy of table 0 that SetupScene stages in shared memory.)
+RT_DEV float PerlinNoise(const DevPerlin* t, double px, double py, double pz)
 {
     const double fx = floor(px), fy = floor(py), fz = floor(pz);
     const float u = (float)(px - fx), v = (float)(py - fy), w = (float)(pz - fz);
@@ -922,16 +924,15 @@ RT_DEV float PerlinNoise(const DevPerlin* __restrict__ t, double px, double py, 
         for (int dj = 0; dj < 2; ++dj)
 #pragma unroll
             for (int dk = 0; dk < 2; ++dk) {
-                const int hsh = __ldg(&t->perm_x[(i + di) & 255]) ^ __ldg(&t->perm_y[(j + dj) & 255]) ^
-                                __ldg(&t->perm_z[(k + dk) & 255]);
-                const float4 c = __ldg(reinterpret_cast<const float4*>(&t->ranvec[hsh][0]));
+                const int hsh = t->perm_x[(i + di) & 255] ^ t->perm_y[(j + dj) & 255] ^ t->perm_z[(k + dk) & 255];
+                const float4 c = *reinterpret_cast<const float4*>(&t->ranvec[hsh][0]);
                 const float wu = di ? uu : 1.0f - uu, wv = dj ? vv : 1.0f - vv, wwt = dk ? ww : 1.0f - ww;
                 accum += wu * wv * wwt * (c.x * (u - di) + c.y * (v - dj) + c.z * (w - dk));
             }
     return accum;
 }
 
-RT_DEV float PerlinTurb(const DevPerlin* __restrict__ t, d3 p, int depth)
+RT_DEV float PerlinTurb(const DevPerlin* t, d3 p, int depth)
 {
     float accum = 0.0f, weight = 1.0f;
     for (int i = 0; i < depth; ++i) {
@@ -994,7 +995,8 @@ template <int FEAT, bool SMEM> RT_DEV f3 TextureValue(const SceneView<SMEM>& sv,
             return make_f3(cs * __ldg(px), cs * __ldg(px + 1), cs * __ldg(px + 2));
         }
         // Texture.h:159-165: marble
-        const DevPerlin* pt = &sv.perlins[__ldg(&t->index)];
+        const int pidx = __ldg(&t->index);
+        const DevPerlin* pt = pidx == 0 ? sv.perlin0 : &sv.perlins[pidx];
         // the phase is ~scale*z (tens of radians): reduce it mod 2 pi in FP64, then sinf
         const double phase = fma((double)__ldg(&t->scale), h.p.z, 10.0 * (double)PerlinTurb(pt, h.p, 7));
         const double k = rint(phase * 0.15915494309189535);
