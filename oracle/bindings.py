@@ -114,6 +114,10 @@ def declare_oracle(lib: C.CDLL) -> None:
     lib.oracle_rng_uniform.argtypes = [C.c_uint32] * 6
     lib.oracle_bvh_topology.restype = C.c_int
     lib.oracle_bvh_topology.argtypes = [C.POINTER(A.rt_scene_desc), C.c_void_p, C.c_int32]
+    lib.oracle_light_pdf.restype = C.c_int
+    lib.oracle_light_pdf.argtypes = [C.POINTER(A.rt_scene_desc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.oracle_light_direction.restype = C.c_int
+    lib.oracle_light_direction.argtypes = [C.POINTER(A.rt_scene_desc), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.oracle_texture_value.restype = C.c_int
     lib.oracle_texture_value.argtypes = [C.POINTER(A.rt_scene_desc), C.c_int, C.c_double, C.c_double, C.c_void_p,
                                          C.c_void_p]

@@ -1170,4 +1170,36 @@ int oracle_texture_value(const rt_scene_desc* scene, int texture, double u, doub
     return 0;
 }
 
+// Importance-sampling pieces, for unit tests of their normalisation: n directions -> the light list's density
+// (mean over the lights, as ScatterImportance mixes it) seen from `origin`; and n directions drawn towards light
+// `light` (index into the light list) from pairs of uniforms.  Return the number of lights, or -1.
+int oracle_light_pdf(const rt_scene_desc* scene, const double* origin, const double* dirs, int n, double* pdf)
+{
+    Scene<double> s;
+    if (!LoadScene(scene, s)) return -1;
+    Stats st;
+    const V3<double> o(origin[0], origin[1], origin[2]);
+    for (int k = 0; k < n; ++k) {
+        const V3<double> d(dirs[3 * k], dirs[3 * k + 1], dirs[3 * k + 2]);
+        double sum = 0.0;
+        for (int l : s.lights) sum += LightPdf(s, l, o, d, st);
+        pdf[k] = s.lights.empty() ? 0.0 : sum / (double)s.lights.size();
+    }
+    return (int)s.lights.size();
+}
+
+int oracle_light_direction(const rt_scene_desc* scene, int light, const double* origin, const double* r12, int n, double* dirs)
+{
+    Scene<double> s;
+    if (!LoadScene(scene, s) || light < 0 || light >= (int)s.lights.size()) return -1;
+    const V3<double> o(origin[0], origin[1], origin[2]);
+    for (int k = 0; k < n; ++k) {
+        const V3<double> d = LightDirection(s, s.lights[(size_t)light], o, r12[2 * k], r12[2 * k + 1]);
+        dirs[3 * k] = d[0];
+        dirs[3 * k + 1] = d[1];
+        dirs[3 * k + 2] = d[2];
+    }
+    return (int)s.lights.size();
+}
+
 } // extern "C"

@@ -34,6 +34,54 @@ def test_light_tables(lib, earth):
         assert i.n_lights == n, (sid, i.n_lights)
 
 
+def test_light_densities_are_normalised_and_match_their_samplers(oracle):
+    """Book 3's quad / sphere pdf_value and random (oracle LightPdf / LightDirection): (1) the density of a light,
+    integrated over all directions from a point, is 1: uniform directions d, mean(pdf(d)) * 4 pi ~ 1; (2) every sampled
+    direction hits the light it was drawn towards (pdf > 0); (3) importance weights of the sampler against its own
+    density average to the light's solid angle measure: E[1 / pdf] over sampled directions = solid angle, and the two
+    estimates of the solid angle agree.  Scene 5 has one sphere light and one quad light, scene 7 one quad."""
+    rng = np.random.default_rng(7)
+    n = 400000
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    for sid, origin in ((7, (278.0, 100.0, 278.0)), (5, (4.0, 0.5, 3.0))):
+        sc = BuiltinScene(sid)
+        o = np.array(origin, np.float64)
+        pdf = np.zeros(n)
+        n_lights = oracle.oracle_light_pdf(sc.desc, o.ctypes.data, np.ascontiguousarray(v).ctypes.data, n, pdf.ctypes.data)
+        assert n_lights == (1 if sid == 7 else 2)
+        hit = pdf > 0
+        se = (pdf * 4 * np.pi).std() / np.sqrt(n)
+        assert abs(pdf.mean() * 4 * np.pi - 1.0) < 5 * se + 0.01, (sid, pdf.mean() * 4 * np.pi, se)
+        omega_uniform = hit.mean() * 4 * np.pi  # solid angle of the union of the lights (they do not overlap here)
+        omega_sampled = 0.0
+        for light in range(n_lights):
+            m = 50000
+            r12 = rng.random((m, 2))
+            dirs = np.zeros((m, 3))
+            assert oracle.oracle_light_direction(sc.desc, light, o.ctypes.data, r12.ctypes.data, m, dirs.ctypes.data) == n_lights
+            p = np.zeros(m)
+            oracle.oracle_light_pdf(sc.desc, o.ctypes.data, dirs.ctypes.data, m, p.ctypes.data)
+            assert (p > 0).mean() > 0.999, (sid, light)  # (a sample on the rim may miss by rounding)
+            # p is the MEAN over the lights; the density of this light's sampler is n_lights * p where only it is hit
+            omega_sampled += float(np.mean(1.0 / (n_lights * p[p > 0])))
+        assert abs(omega_sampled - omega_uniform) < 0.05 * omega_uniform, (sid, omega_sampled, omega_uniform)
+
+
+def test_the_reference_lambertian_lobe_is_two_cos_cubed_over_pi():
+    """The density ScatterImportance weighs with: the direction of N + (uniform point in the unit ball)
+    (Material.h:14-24,68-86) has density 2 cos^3(theta) / pi -- checked against a histogram of cos(theta)."""
+    rng = np.random.default_rng(11)
+    pts = rng.uniform(-1, 1, size=(600000, 3))
+    pts = pts[(pts ** 2).sum(1) < 1.0]
+    d = pts + np.array([0.0, 0.0, 1.0])
+    c = d[:, 2] / np.linalg.norm(d, axis=1)
+    hist, edges = np.histogram(c, bins=20, range=(0.0, 1.0), density=True)
+    mid = 0.5 * (edges[1:] + edges[:-1])
+    # density in cos(theta): p(omega) * 2 pi = 4 cos^3
+    assert np.allclose(hist, 4.0 * mid ** 3, rtol=0.06, atol=0.02)
+
+
 @pytest.mark.parametrize("sid,W,H", [(7, 32, 32), (5, 48, 27)])
 def test_oracle_importance_is_unbiased_and_less_noisy(oracle, sid, W, H):
     """Same mean image as the reference's scattering, lower variance: 4 batches of 128 spp each way."""
